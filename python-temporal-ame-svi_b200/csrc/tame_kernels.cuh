@@ -1,0 +1,743 @@
+// tame_kernels.cuh -- sm_100a FP64 kernels of the Temporal-AME variational update loop.
+//
+// Reference formulas (file:line under /root/reference):
+//   observation terms   src/inference/structured_mf.py:289-326 (== naive_mf.py:284-376)
+//   node update         src/inference/structured_mf.py:220-287, src/inference/naive_mf.py:207-282
+//   ELBO                src/inference/structured_mf.py:115-209, src/inference/naive_mf.py:89-191
+//   reconstruction MSE  src/models/temporal_ame.py:255-291, src/models/static_ame.py:189-238
+//
+// Data layout in HBM (all FP64, row-major):
+//   Y    (nloc, n, T, 2)   the reference layout; for a fixed row the (j,t) pairs are contiguous 16-byte dyads,
+//                          so a warp with lane <-> t streams 512 contiguous bytes per partner j.
+//   Xm   (n, T, D)         D = 2 + 2R, x = [a, b, U(R), V(R)]
+//   Xc   (n, T, D, D)
+//   H    (nloc, T, 2R)     partner contraction  [ sum_j w0*V_j (R) , sum_j w1*U_j (R) ]  ("z order")
+//   hab  (nloc, T, 2)      sum_j w0, sum_j w1  (sweep invariant)
+//   tot  (T, 2R + 4R^2)    g = sum_j z_j, G = sum_j z_j z_j'  with z_j = [V_j, U_j]
+//
+// The Gauss-Seidel schedule of the reference is kept exactly: cell (i,t) sees new means of (j<i, t) and
+// (i, t-1), old means of (j>i, t) and (i, t+1).  Parallelism comes from (a) the partner reductions
+// (k_contract), (b) a systolic pipeline over time (k_chain: warp t owns time step t and walks the nodes in
+// order, handing its new mean to warp t+1), (c) the streaming ELBO pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#define TAME_WIN 64          // inline window of the chain kernel (nodes)
+#define TAME_CHAIN_WPC 8     // warps (time steps) per chain CTA
+#define TAME_SPIN_LIMIT (1 << 24)
+
+struct TameParams {
+    int n, T, nloc, world, rank, panel, mode;
+    double lr, p0, p1, q;     // R_inv = [[p0,q],[q,p1]]
+    const double* Y;          // local rows
+    double* Xm;
+    double* Xc;
+    double* H;
+    double* hab;
+    double* tot;
+    const double* cst;        // 6 DxD matrices: S0inv, Qinv, Phi'QinvPhi, QinvPhi, Phi'Qinv, Phi
+    int* progress;            // (T) nodes finished in this sweep by the warp of time t
+    int* abort_flag;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 tame_ld_stream2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double tame_ld_cg(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ void tame_st_cg(double* p, double v) { __stcg(p, v); }
+__device__ __forceinline__ int tame_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tame_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// local row of global node i / global node of local row (panel-cyclic ownership)
+__device__ __forceinline__ int tame_lrow(int i, int panel, int world) {
+    int b = i / panel;
+    return (b / world) * panel + (i - b * panel);
+}
+__device__ __forceinline__ int tame_grow(int l, int panel, int world, int rank) {
+    int lb = l / panel;
+    return (lb * world + rank) * panel + (l - lb * panel);
+}
+__device__ __forceinline__ bool tame_owned(int i, int panel, int world, int rank) { return ((i / panel) % world) == rank; }
+
+// ------------------------------------------------------------------------------------------------------
+// moment totals per time step:  g[x] = sum_j z_j[x],  G[x][y] = sum_j z_j[x] z_j[y],  z_j = [V_j, U_j]
+// (the partner sums of structured_mf.py:310-323 in closed form)
+// k_totals_partial: grid (T, NS), block 320 (>= TOT for R=8: 272); k_totals_final: grid T.
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+struct TameTot {
+    static constexpr int NV = 2 * R;
+    static constexpr int TOT = NV + NV * NV;
+};
+
+template <int R>
+__device__ __forceinline__ int tame_zidx(int x) {  // index into x=[a,b,U,V] of component x of z=[V,U]
+    return x < R ? 2 + R + x : 2 + (x - R);
+}
+
+template <int R>
+__global__ void __launch_bounds__(320) k_totals_partial(TameParams P, double* partial, int NS) {
+    constexpr int D = 2 + 2 * R, NV = 2 * R, TOT = TameTot<R>::TOT;
+    const int t = blockIdx.x, s = blockIdx.y, e = threadIdx.x;
+    const int chunk = (P.n + NS - 1) / NS;
+    const int jb = s * chunk, je = min(P.n, jb + chunk);
+    if (e >= TOT) return;
+    int xa, xb = -1;
+    if (e < NV) {
+        xa = tame_zidx<R>(e);
+    } else {
+        int f = e - NV;
+        xa = tame_zidx<R>(f / NV);
+        xb = tame_zidx<R>(f % NV);
+    }
+    double acc = 0.0;
+    for (int j = jb; j < je; ++j) {
+        const double* m = P.Xm + ((size_t)j * P.T + t) * D;
+        double va = m[xa];
+        acc += (xb < 0) ? va : va * m[xb];
+    }
+    partial[((size_t)t * NS + s) * TOT + e] = acc;
+}
+
+template <int R>
+__global__ void k_totals_final(TameParams P, const double* partial, int NS) {
+    constexpr int TOT = TameTot<R>::TOT;
+    const int t = blockIdx.x;
+    for (int e = threadIdx.x; e < TOT; e += blockDim.x) {
+        double acc = 0.0;
+        for (int s = 0; s < NS; ++s) acc += partial[((size_t)t * NS + s) * TOT + e];
+        P.tot[(size_t)t * TOT + e] = acc;
+    }
+    if (threadIdx.x == 0) P.progress[t] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_contract: H[k,t,:] (+)= sum_{j in [j0,j1), (tri ? j>k : j!=k)} ( w0(k,j,t) * V_j(t) , w1(k,j,t) * U_j(t) )
+// with w0 = p0*y0 + q*y1, w1 = q*y0 + p1*y1  -- the [U,V] rows of sum_j J'R^-1 y_ij (structured_mf.py:324).
+// One pass over Y[k0:k1, j0:j1].  lane <-> t (512 contiguous bytes of Y per partner), RW rows per warp,
+// partner vectors staged in shared memory per chunk of JC partners and shared by the CTA's 8*RW rows.
+// grid (ceil(T/32), ceil((k1-k0)/(8*RW))), block 256.
+// ------------------------------------------------------------------------------------------------------
+template <int R, int RW>
+__global__ void __launch_bounds__(256) k_contract(TameParams P, int k0, int k1, int j0, int j1, int tri, int accumulate) {
+    constexpr int D = 2 + 2 * R, NV = 2 * R, JC = 8, RT = 8 * RW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*Ms)[JC][NV][32] = reinterpret_cast<double (*)[JC][NV][32]>(smem_raw);   // [2][JC][NV][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t0 = blockIdx.x * 32, t = t0 + lane;
+    const bool tv = t < P.T;
+    const int kbase = k0 + blockIdx.y * RT;
+    if (!tame_owned(kbase, P.panel, P.world, P.rank)) return;   // RT divides the panel size
+    const int kw = kbase + warp * RW;
+
+    double accA[RW][R], accB[RW][R];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr)
+#pragma unroll
+        for (int a = 0; a < R; ++a) accA[rr][a] = accB[rr][a] = 0.0;
+
+    const double* yrow[RW];
+    bool rv[RW];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+        int k = kw + rr;
+        rv[rr] = (k < k1) && tv;
+        int l = tame_lrow(min(k, P.n - 1), P.panel, P.world);
+        yrow[rr] = P.Y + ((size_t)l * P.n * P.T + (tv ? t : 0)) * 2;
+    }
+    const size_t jstride = (size_t)P.T * 2;
+
+    int jstart = j0;
+    if (tri) jstart = max(j0, ((kbase + 1) / JC) * JC);
+    const int nchunks = (j1 > jstart) ? (j1 - jstart + JC - 1) / JC : 0;
+
+    auto stage = [&](int buf, int jc) {
+        // 4096/NV.. elements: (jj, x, tl); thread -> tl = e%32 (coalesced smem), x, jj
+        for (int e = threadIdx.x; e < JC * NV * 32; e += 256) {
+            int tl = e & 31, x = (e >> 5) % NV, jj = (e >> 5) / NV;
+            int j = jc + jj, tt = t0 + tl;
+            double v = 0.0;
+            if (j < j1 && tt < P.T) v = P.Xm[((size_t)j * P.T + tt) * D + tame_zidx<R>(x)];
+            Ms[buf][jj][x][tl] = v;
+        }
+    };
+
+    if (nchunks > 0) stage(0, jstart);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int jc = jstart + c * JC, buf = c & 1;
+        if (c + 1 < nchunks) stage(buf ^ 1, jc + JC);
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) {
+            double w0[RW], w1[RW];
+#pragma unroll
+            for (int rr = 0; rr < RW; ++rr) {
+                const int j = jc + jj, k = kw + rr;
+                const bool ok = rv[rr] && (j < j1) && (tri ? (j > k) : (j != k));
+                const double2 y = ok ? tame_ld_stream2(yrow[rr] + (size_t)j * jstride) : make_double2(0.0, 0.0);
+                w0[rr] = P.p0 * y.x + P.q * y.y;
+                w1[rr] = P.q * y.x + P.p1 * y.y;
+            }
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+                double zv = Ms[buf][jj][a][lane];       // V_j[a]
+                double zu = Ms[buf][jj][R + a][lane];   // U_j[a]
+#pragma unroll
+                for (int rr = 0; rr < RW; ++rr) {
+                    accA[rr][a] = fma(w0[rr], zv, accA[rr][a]);
+                    accB[rr][a] = fma(w1[rr], zu, accB[rr][a]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+        int k = kw + rr;
+        if (k < k1 && tv) {
+            double* h = P.H + ((size_t)tame_lrow(k, P.panel, P.world) * P.T + t) * NV;
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+                h[a] = accumulate ? h[a] + accA[rr][a] : accA[rr][a];
+                h[R + a] = accumulate ? h[R + a] + accB[rr][a] : accB[rr][a];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// warp-level in-place Gauss-Jordan inverse of a symmetric positive-definite DxD matrix.
+// lane c (< D) holds column c in col[0..D-1].  At step k every lane publishes its element of pivot row k,
+// the whole row is read back as a shared-memory broadcast, and column k is reconstructed from the row by the
+// (anti)symmetry of the partially swept matrix ( M[r][k] = -M[k][r] for swept r<k, +M[k][r] otherwise ).
+// Returns sum_k log(pivot_k) = logdet when WANT_LOGDET.  rowb: 2*(D+2) doubles of per-warp shared memory.
+// ------------------------------------------------------------------------------------------------------
+template <int D, bool WANT_LOGDET>
+__device__ __forceinline__ double tame_gj_inverse(double (&col)[D], double* rowb, int lane) {
+    constexpr int RB = D + 2;
+    double logdet = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double* rb = rowb + (k & 1) * RB;
+        if (lane < D) rb[lane] = col[k];
+        __syncwarp();
+        double rk[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) rk[r] = rb[r];
+        const double piv = 1.0 / rk[k];
+        if (WANT_LOGDET) logdet += log(rk[k]);
+        const double s = col[k] * piv;
+        const bool isk = (lane == k);
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            if (r == k) continue;
+            const double f = (r < k) ? -rk[r] : rk[r];
+            col[r] = isk ? (-f * piv) : fma(-f, s, col[r]);
+        }
+        col[k] = isk ? piv : s;
+    }
+    return logdet;
+}
+
+// per-warp shared memory of the chain kernel
+template <int R>
+struct TameChainSmem {
+    static constexpr int D = 2 + 2 * R, NV = 2 * R, MP = NV + 2, TOT = TameTot<R>::TOT, DP = D + 1;
+    double ring[TAME_WIN][MP];   // z = [V,U] of the window's already updated nodes at this warp's time step
+    double tot[TOT];             // g (NV) then G (NV x NV)
+    double rowb[2 * (D + 2)];
+    double Cm[D * DP];
+    double Cf[D * D];
+    double wbuf[TAME_WIN * 2];
+    double mold[D], mnew[D], mprev[D], mnext[D], hvec[D], hin[NV];
+};
+
+// z component x of a mean vector held in shared memory
+template <int R>
+__device__ __forceinline__ double tame_zof(const double* m, int x) { return m[tame_zidx<R>(x)]; }
+
+// tot += sign * (z, z z')
+template <int R>
+__device__ __forceinline__ void tame_tot_update(double* tot, const double* m, double sign, int lane) {
+    constexpr int NV = 2 * R, TOT = TameTot<R>::TOT;
+    for (int e = lane; e < TOT; e += 32) {
+        double term;
+        if (e < NV) {
+            term = tame_zof<R>(m, e);
+        } else {
+            int f = e - NV;
+            term = tame_zof<R>(m, f / NV) * tame_zof<R>(m, f % NV);
+        }
+        tot[e] = fma(sign, term, tot[e]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_chain: the Gauss-Seidel chain over nodes [i0,i1) (one panel, i1-i0 <= TAME_WIN, owned by this rank).
+// Warp <-> time step t.  For each node in order the warp
+//   1. removes the node's own term from the running totals, builds P = P_obs + prior/AR precision
+//      (structured_mf.py:246-264) and inverts it (:267),
+//   2. applies the factorisation mask / symmetrisation / jitter (:270-277) or the naive rule (naive_mf.py:268-274),
+//   3. assembles h: static partner part H + inline window (partners of this panel already updated) + AR terms
+//      with the NEW mean of (i,t-1) handed over by warp t-1 and the OLD mean of (i,t+1),
+//   4. writes the damped mean/covariance (:282-287), publishes progress, restores the totals with the new mean.
+// Launched cooperatively (all CTAs co-resident): warps spin on their predecessor's progress counter.
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int i0, int i1) {
+    using S = TameChainSmem<R>;
+    constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP, NE = (D * D + 31) / 32, NWS = TAME_WIN / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cstQP = reinterpret_cast<double*>(smem_raw);          // QinvPhi   (D*D)
+    double* cstPQ = cstQP + D * D;                                // Phi'Qinv  (D*D)
+    S* warps = reinterpret_cast<S*>(cstPQ + D * D);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < 2 * D * D; e += blockDim.x) cstQP[e] = P.cst[3 * D * D + e];
+    __syncthreads();
+    const int t = blockIdx.x * TAME_CHAIN_WPC + warp;
+    if (t >= P.T) return;
+    S& sm = warps[warp];
+    const int T = P.T;
+    const bool has_prev = t > 0, has_next = t < T - 1;
+    const int c = lane;   // column / component owned by this lane
+
+    // constant part of the precision, column c:  (t==0 ? S0inv : Qinv) + (t<T-1 ? Phi'QinvPhi : 0)
+    double cstcol[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double v = 0.0;
+        if (c < D) {
+            v = has_prev ? P.cst[1 * D * D + k * D + c] : P.cst[0 * D * D + k * D + c];
+            if (has_next) v += P.cst[2 * D * D + k * D + c];
+        }
+        cstcol[k] = v;
+    }
+    for (int e = lane; e < TOT; e += 32) sm.tot[e] = P.tot[(size_t)t * TOT + e];
+    // scale pattern of P_obs (see header): rows x<R of the z-block use sA, rows x>=R use sB
+    double sA, sB;
+    if (c == 0) { sA = P.p0; sB = P.q; }
+    else if (c == 1) { sA = P.q; sB = P.p1; }
+    else if (c - 2 < R) { sA = P.p0; sB = P.q; }
+    else { sA = P.q; sB = P.p1; }
+    const double m1 = (double)(P.n - 1);
+    const double lr = P.lr, om = 1.0 - P.lr;
+    __syncwarp();
+
+    // prefetch registers for node i
+    double2 yv[NWS];
+    double cold[NE];
+    double hbase = 0.0, mold = 0.0, mnext = 0.0;
+    auto prefetch = [&](int i) {
+        const int l = tame_lrow(i, P.panel, P.world);
+#pragma unroll
+        for (int s = 0; s < NWS; ++s) {
+            int j = i0 + lane + 32 * s;
+            yv[s] = (j < i) ? tame_ld_stream2(P.Y + (((size_t)l * P.n + j) * T + t) * 2) : make_double2(0.0, 0.0);
+        }
+        const double* cp = P.Xc + ((size_t)i * T + t) * D * D;
+#pragma unroll
+        for (int m = 0; m < NE; ++m) {
+            int e = lane + 32 * m;
+            cold[m] = (e < D * D) ? __ldcs(cp + e) : 0.0;
+        }
+        if (c < 2) hbase = P.hab[((size_t)l * T + t) * 2 + c];
+        else if (c < D) hbase = __ldcg(P.H + ((size_t)l * T + t) * NV + (c - 2));
+        if (c < D) {
+            mold = tame_ld_cg(P.Xm + ((size_t)i * T + t) * D + c);
+            mnext = has_next ? tame_ld_cg(P.Xm + ((size_t)i * T + t + 1) * D + c) : 0.0;
+        }
+    };
+    prefetch(i0);
+
+    for (int i = i0; i < i1; ++i) {
+        // ---- take the prefetched values, start the next node's loads
+        double2 ycur[NWS];
+#pragma unroll
+        for (int s = 0; s < NWS; ++s) ycur[s] = yv[s];
+        double ccur[NE];
+#pragma unroll
+        for (int m = 0; m < NE; ++m) ccur[m] = cold[m];
+        const double hb = hbase, mo = mold, mn = mnext;
+        if (i + 1 < i1) prefetch(i + 1);
+
+        if (c < D) { sm.mold[c] = mo; sm.mnext[c] = mn; }
+        __syncwarp();
+        tame_tot_update<R>(sm.tot, sm.mold, -1.0, lane);
+        __syncwarp();
+
+        // ---- precision column c
+        double col[D];
+        {
+            const double* g = sm.tot;
+            const double* G = sm.tot + NV;
+            if (c < 2) {
+                col[0] = (c == 0) ? P.p0 * m1 : P.q * m1;
+                col[1] = (c == 0) ? P.q * m1 : P.p1 * m1;
+#pragma unroll
+                for (int x = 0; x < NV; ++x) col[2 + x] = ((x < R) ? sA : sB) * g[x];
+            } else if (c < D) {
+                const int y = c - 2;
+                col[0] = sA * g[y];
+                col[1] = sB * g[y];
+#pragma unroll
+                for (int x = 0; x < NV; ++x) col[2 + x] = ((x < R) ? sA : sB) * G[x * NV + y];
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; ++k) col[k] = 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) col[k] += cstcol[k];
+        }
+        double pdiag = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) pdiag = (k == c) ? col[k] : pdiag;
+
+        // ---- inline window: partners of this panel that were already updated (new means, same time step)
+        {
+#pragma unroll
+            for (int s = 0; s < NWS; ++s) {
+                int slot = lane + 32 * s;
+                sm.wbuf[slot * 2 + 0] = P.p0 * ycur[s].x + P.q * ycur[s].y;
+                sm.wbuf[slot * 2 + 1] = P.q * ycur[s].x + P.p1 * ycur[s].y;
+            }
+            __syncwarp();
+            const int cnt = i - i0;
+            const int x = lane & 15, half = lane >> 4;
+            double acc = 0.0;
+            if (x < NV) {
+                const int wsel = (x < R) ? 0 : 1;
+                for (int jj = half; jj < cnt; jj += 2) acc = fma(sm.wbuf[jj * 2 + wsel], sm.ring[jj][x], acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (lane < NV) sm.hin[lane] = acc;
+        }
+
+        // ---- inverse
+        tame_gj_inverse<D, false>(col, sm.rowb, lane);
+
+        // ---- factorisation rule -> row c of the new covariance in crow[]
+        double crow[D];
+        if (P.mode == 2 /*BAD*/) {
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+                if ((k < 2) != (c < 2)) col[k] = 0.0;
+        }
+        if (c < D) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) sm.Cm[k * DP + c] = col[k];
+        }
+        __syncwarp();
+        if (c < D) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                double rv = sm.Cm[c * DP + k];
+                crow[k] = (P.mode == 0) ? rv : (0.5 * (rv + col[k]) + ((k == c) ? 1e-6 : 0.0));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) crow[k] = 0.0;
+        }
+
+        // ---- wait for (i, t-1), fetch its new mean
+        if (has_prev) {
+            if (lane == 0) {
+                int spins = 0;
+                while (tame_ld_acquire(P.progress + (t - 1)) <= i) {
+                    if (++spins > TAME_SPIN_LIMIT) { atomicExch(P.abort_flag, 1); break; }
+                    if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+                }
+            }
+            __syncwarp();
+            if (c < D) sm.mprev[c] = tame_ld_cg(P.Xm + ((size_t)i * T + t - 1) * D + c);
+        }
+        __syncwarp();
+
+        // ---- natural parameter
+        double hval = 0.0;
+        if (c < D) {
+            hval = hb + ((c >= 2) ? sm.hin[c - 2] : 0.0);
+            if (has_prev) {
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) a = fma(cstQP[c * D + k], sm.mprev[k], a);
+                hval += a;
+            }
+            if (has_next) {
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) a = fma(cstPQ[c * D + k], sm.mnext[k], a);
+                hval += a;
+            }
+            sm.hvec[c] = hval;
+        }
+        __syncwarp();
+
+        // ---- mean, damped write, hand-over
+        if (c < D) {
+            double mu = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) mu = fma(crow[k], sm.hvec[k], mu);
+            const double mnew = lr * mu + om * mo;
+            tame_st_cg(P.Xm + ((size_t)i * T + t) * D + c, mnew);
+            sm.mnew[c] = mnew;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) tame_st_release(P.progress + t, i + 1);
+
+        // ---- covariance, damped write (coalesced through shared memory)
+        if (c < D) {
+            if (P.mode == 0) {
+                const double dinv = 1.0 / (pdiag + 1e-8);
+#pragma unroll
+                for (int k = 0; k < D; ++k) sm.Cf[c * D + k] = (k == c) ? dinv : 0.0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; ++k) sm.Cf[c * D + k] = crow[k];
+            }
+        }
+        __syncwarp();
+        {
+            double* cp = P.Xc + ((size_t)i * T + t) * D * D;
+#pragma unroll
+            for (int m = 0; m < NE; ++m) {
+                int e = lane + 32 * m;
+                if (e < D * D) __stcs(cp + e, lr * sm.Cf[e] + om * ccur[m]);
+            }
+        }
+        // ---- totals with the new mean, window ring
+        tame_tot_update<R>(sm.tot, sm.mnew, 1.0, lane);
+        if (lane < NV) sm.ring[i - i0][lane] = tame_zof<R>(sm.mnew, lane);
+        __syncwarp();
+    }
+    for (int e = lane; e < TOT; e += 32) P.tot[(size_t)t * TOT + e] = sm.tot[e];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_llmse: fused expected-log-likelihood quadratic form + reconstruction error, one pass over Y.
+//   e0 = y0 - (a_i + b_j + U_i.V_j), e1 = y1 - (a_j + b_i + U_j.V_i)        static_ame.py:226-236
+//   sq   += e0^2 + e1^2                        for all i != j               temporal_ame.py:284-290
+//   quad += p0 e0^2 + 2 q e0 e1 + p1 e1^2      for i < j only               structured_mf.py:136-139
+// Same tiling as k_contract (lane <-> t, RW rows per warp, partner state staged in shared memory).
+// grid (ceil(T/32), ceil(nloc/(8*RW))), block 256; partial (grid.y*grid.x, 2).
+// ------------------------------------------------------------------------------------------------------
+template <int R, int RW>
+__global__ void __launch_bounds__(256) k_llmse(TameParams P, double* partial) {
+    constexpr int D = 2 + 2 * R, JC = 8, RT = 8 * RW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*Xs)[JC][D][32] = reinterpret_cast<double (*)[JC][D][32]>(smem_raw);     // [2][JC][D][32]
+    __shared__ double red[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t0 = blockIdx.x * 32, t = t0 + lane;
+    const bool tv = t < P.T;
+    const int lw = blockIdx.y * RT + warp * RW;
+
+    double oa[RW], ob[RW], oU[RW][R], oV[RW][R];
+    const double* yrow[RW];
+    int gi[RW];
+    bool rv[RW];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+        int l = lw + rr;
+        rv[rr] = (l < P.nloc) && tv;
+        l = min(l, P.nloc - 1);
+        gi[rr] = tame_grow(l, P.panel, P.world, P.rank);
+        const double* m = P.Xm + ((size_t)gi[rr] * P.T + (tv ? t : 0)) * D;
+        oa[rr] = m[0];
+        ob[rr] = m[1];
+#pragma unroll
+        for (int a = 0; a < R; ++a) { oU[rr][a] = m[2 + a]; oV[rr][a] = m[2 + R + a]; }
+        yrow[rr] = P.Y + ((size_t)l * P.n * P.T + (tv ? t : 0)) * 2;
+    }
+    const size_t jstride = (size_t)P.T * 2;
+    double sq = 0.0, quad = 0.0;
+
+    auto stage = [&](int buf, int jc) {
+        for (int e = threadIdx.x; e < JC * D * 32; e += 256) {
+            int tl = e & 31, k = (e >> 5) % D, jj = (e >> 5) / D;
+            int j = jc + jj, tt = t0 + tl;
+            double v = 0.0;
+            if (j < P.n && tt < P.T) v = P.Xm[((size_t)j * P.T + tt) * D + k];
+            Xs[buf][jj][k][tl] = v;
+        }
+    };
+    const int nchunks = (P.n + JC - 1) / JC;
+    stage(0, 0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int jc = c * JC, buf = c & 1;
+        if (c + 1 < nchunks) stage(buf ^ 1, jc + JC);
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) {
+            const int j = jc + jj;
+            double2 y[RW];
+#pragma unroll
+            for (int rr = 0; rr < RW; ++rr) {
+                const bool ok = rv[rr] && (j < P.n) && (j != gi[rr]);
+                y[rr] = ok ? tame_ld_stream2(yrow[rr] + (size_t)j * jstride) : make_double2(0.0, 0.0);
+            }
+            const double aj = Xs[buf][jj][0][lane], bj = Xs[buf][jj][1][lane];
+            double d0[RW], d1[RW];
+#pragma unroll
+            for (int rr = 0; rr < RW; ++rr) { d0[rr] = 0.0; d1[rr] = 0.0; }
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+                const double uj = Xs[buf][jj][2 + a][lane], vj = Xs[buf][jj][2 + R + a][lane];
+#pragma unroll
+                for (int rr = 0; rr < RW; ++rr) {
+                    d0[rr] = fma(oU[rr][a], vj, d0[rr]);
+                    d1[rr] = fma(uj, oV[rr][a], d1[rr]);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < RW; ++rr) {
+                const bool ok = rv[rr] && (j < P.n) && (j != gi[rr]);
+                if (ok) {
+                    const double e0 = y[rr].x - ((oa[rr] + bj) + d0[rr]);
+                    const double e1 = y[rr].y - ((aj + ob[rr]) + d1[rr]);
+                    sq += e0 * e0 + e1 * e1;
+                    if (j > gi[rr]) quad += P.p0 * e0 * e0 + 2.0 * P.q * e0 * e1 + P.p1 * e1 * e1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    }
+    if (lane == 0) { red[0][warp] = sq; red[1][warp] = quad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0, qd = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { s += red[0][w]; qd += red[1][w]; }
+        size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        partial[b * 2 + 0] = s;
+        partial[b * 2 + 1] = qd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_cellterms: per (i,t) block terms of the ELBO, one warp per owned cell.
+//   ent   = 0.5 (d (1+log 2pi) + logdet X_cov[i,t])                                    structured_mf.py:202-209
+//   t==0 : lp0 = -0.5 (logdet S0 + mu' S0inv mu + tr(S0inv X_cov) + d log 2pi)         :152-173
+//   t>0  : lpt = -0.5 (logdet Q + (mu_t - Phi mu_{t-1})' Qinv (..) + tr(Qinv X_cov) + d log 2pi)   :175-200
+//   tr    = trace X_cov[i,t]   (for the "simplified" correction, :142-144)
+// block 256 (8 warps); partial (gridDim.x, 4) = {lp0, lpt, ent, tr}.
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0, double logdetQ, double* partial) {
+    constexpr int D = 2 + 2 * R, NE = (D * D + 31) / 32;
+    __shared__ double Cm[8][D * D];
+    __shared__ double rowb[8][2 * (D + 2)];
+    __shared__ double vec[8][2 * D];
+    __shared__ double red[8][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double LOG2PI = 1.8378770664093454835606594728112;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const long ncell = (long)P.nloc * P.T;
+    for (long cell = (long)blockIdx.x * 8 + warp; cell < ncell; cell += (long)gridDim.x * 8) {
+        const int l = (int)(cell / P.T), t = (int)(cell % P.T);
+        const int i = tame_grow(l, P.panel, P.world, P.rank);
+        const double* cp = P.Xc + ((size_t)i * P.T + t) * D * D;
+#pragma unroll
+        for (int m = 0; m < NE; ++m) {
+            int e = lane + 32 * m;
+            if (e < D * D) Cm[warp][e] = cp[e];
+        }
+        const int c = lane;
+        if (c < D) {
+            double mt = P.Xm[((size_t)i * P.T + t) * D + c];
+            vec[warp][c] = mt;
+            vec[warp][D + c] = (t > 0) ? P.Xm[((size_t)i * P.T + t - 1) * D + c] : 0.0;
+        }
+        __syncwarp();
+        const double* A = P.cst + (t == 0 ? 0 : 1) * D * D;   // S0inv or Qinv
+        const double* Phi = P.cst + 5 * D * D;
+        double col[D];
+        double tr = 0.0, trA = 0.0, resid = 0.0;
+        if (c < D) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                col[k] = Cm[warp][k * D + c];
+                trA = fma(A[c * D + k], col[k], trA);       // sum_k A[c][k] * cov[k][c]
+                tr = (k == c) ? col[k] : tr;
+            }
+            resid = vec[warp][c];
+            if (t > 0) {
+                double pm = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) pm = fma(Phi[c * D + k], vec[warp][D + k], pm);
+                resid -= pm;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) col[k] = 0.0;
+        }
+        __syncwarp();
+        if (c < D) vec[warp][c] = resid;
+        __syncwarp();
+        double quad = 0.0;
+        if (c < D) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) a = fma(A[c * D + k], vec[warp][k], a);
+            quad = resid * a;
+        }
+        const double logdet = tame_gj_inverse<D, true>(col, rowb[warp], lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tr += __shfl_xor_sync(0xffffffffu, tr, o);
+            trA += __shfl_xor_sync(0xffffffffu, trA, o);
+            quad += __shfl_xor_sync(0xffffffffu, quad, o);
+        }
+        if (lane == 0) {
+            const double lp = -0.5 * ((t == 0 ? logdetS0 : logdetQ) + quad + trA + D * LOG2PI);
+            if (t == 0) acc[0] += lp; else acc[1] += lp;
+            acc[2] += 0.5 * (D * (1.0 + LOG2PI) + logdet);
+            acc[3] += tr;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+    }
+}
+
+// function table of one latent dimension
+struct TameOps {
+    int r;
+    size_t chain_smem;
+    int tot;
+    void (*totals)(const TameParams&, double* partial, int NS, cudaStream_t);
+    void (*contract)(const TameParams&, int k0, int k1, int j0, int j1, int tri, int accumulate, cudaStream_t);
+    cudaError_t (*chain)(const TameParams&, int i0, int i1, cudaStream_t);
+    int (*chain_max_T)();
+    void (*llmse)(const TameParams&, double* partial, int* nblocks, cudaStream_t);
+    void (*cellterms)(const TameParams&, double logdetS0, double logdetQ, double* partial, int nblocks, cudaStream_t);
+    int (*llmse_blocks)(const TameParams&);
+};
+const TameOps* tame_get_ops(int r);
+void tame_count_launch(int n);

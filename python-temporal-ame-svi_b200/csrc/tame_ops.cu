@@ -1,0 +1,83 @@
+// tame_ops.cu -- instantiates the kernels of tame_kernels.cuh for one latent dimension (-DTAME_R=r) and
+// exports their launchers through a function table; tame_api.cu picks the table by cfg.r.
+#include "tame_kernels.cuh"
+
+#ifndef TAME_R
+#error "compile with -DTAME_R=<latent dim>"
+#endif
+
+namespace {
+constexpr int R = TAME_R;
+constexpr int RW = 4;
+
+void launch_totals(const TameParams& P, double* partial, int NS, cudaStream_t st) {
+    k_totals_partial<R><<<dim3(P.T, NS), 320, 0, st>>>(P, partial, NS);
+    k_totals_final<R><<<P.T, 128, 0, st>>>(P, partial, NS);
+    tame_count_launch(2);
+}
+
+void launch_contract(const TameParams& P, int k0, int k1, int j0, int j1, int tri, int accumulate, cudaStream_t st) {
+    if (k1 <= k0 || j1 <= j0) return;
+    dim3 grid((P.T + 31) / 32, (k1 - k0 + 8 * RW - 1) / (8 * RW));
+    constexpr size_t smem = 2 * 8 * (2 * R) * 32 * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_contract<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_contract<R, RW><<<grid, 256, smem, st>>>(P, k0, k1, j0, j1, tri, accumulate);
+    tame_count_launch(1);
+}
+
+size_t chain_smem_bytes() { return 2 * (2 + 2 * R) * (2 + 2 * R) * sizeof(double) + TAME_CHAIN_WPC * sizeof(TameChainSmem<R>); }
+
+cudaError_t launch_chain(const TameParams& P, int i0, int i1, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = chain_smem_bytes();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    TameParams p = P;
+    void* args[] = {(void*)&p, (void*)&i0, (void*)&i1};
+    dim3 grid((P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC);
+    tame_count_launch(1);
+    return cudaLaunchCooperativeKernel((void*)k_chain<R>, grid, dim3(TAME_CHAIN_WPC * 32), args, smem, st);
+}
+
+int chain_max_T() {
+    int dev = 0, sms = 0, per = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<R>, TAME_CHAIN_WPC * 32, chain_smem_bytes());
+    return sms * per * TAME_CHAIN_WPC;
+}
+
+int llmse_blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 8 * RW - 1) / (8 * RW)); }
+
+void launch_llmse(const TameParams& P, double* partial, int* nblocks, cudaStream_t st) {
+    dim3 grid((P.T + 31) / 32, (P.nloc + 8 * RW - 1) / (8 * RW));
+    constexpr size_t smem = 2 * 8 * (2 + 2 * R) * 32 * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_llmse<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_llmse<R, RW><<<grid, 256, smem, st>>>(P, partial);
+    *nblocks = grid.x * grid.y;
+    tame_count_launch(1);
+}
+
+void launch_cellterms(const TameParams& P, double logdetS0, double logdetQ, double* partial, int nblocks, cudaStream_t st) {
+    k_cellterms<R><<<nblocks, 256, 0, st>>>(P, logdetS0, logdetQ, partial);
+    tame_count_launch(1);
+}
+}  // namespace
+
+#define TAME_CAT2(a, b) a##b
+#define TAME_CAT(a, b) TAME_CAT2(a, b)
+extern const TameOps TAME_CAT(tame_ops_r, TAME_R) = {
+    R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, chain_max_T,
+    launch_llmse, launch_cellterms, llmse_blocks};
