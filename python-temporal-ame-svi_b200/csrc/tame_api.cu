@@ -19,6 +19,7 @@
 // ------------------------------------------------------------------------------------------------------
 // bookkeeping
 // ------------------------------------------------------------------------------------------------------
+static_assert(sizeof(tame_config) == 120, "tame_config layout is part of the ABI (ctypes mirror in _lib.py)");
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 void tame_count_launch(int n) { g_launches += n; }

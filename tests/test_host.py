@@ -117,4 +117,4 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/tame_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     assert b"sm_100a" in lib.tame_version()
-    assert ctypes.sizeof(_lib.TameConfig) == 112
+    assert ctypes.sizeof(_lib.TameConfig) == 120
