@@ -125,19 +125,25 @@ static void ev_mark(tame_handle* h, int kind) {
     h->ev_kind[h->ev_used] = kind;
     ++h->ev_used;
 }
-// after a stream sync: fold the recorded intervals into the per-kind totals; returns the whole span
-static double ev_fold(tame_handle* h, double* contract, double* chain, double* llmse) {
-    double span = 0;
+// after a stream sync: fold the recorded intervals into the per-kind totals of the last iteration.
+// kinds: 0 other (sweep side), 1 contract, 2 chain, 3 llmse, 4 sweep/ELBO boundary, 5 other (ELBO side)
+static void ev_fold(tame_handle* h) {
+    double sweep = 0, elbo = 0, contract = 0, chain = 0, llmse = 0;
+    bool in_elbo = true;
+    for (size_t k = 0; k < h->ev_used; ++k)
+        if (h->ev_kind[k] == 4) in_elbo = false;   // a sweep was recorded: intervals before the boundary are its
     for (size_t k = 0; k + 1 < h->ev_used; ++k) {
         float ms = 0;
         cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]);
-        span += ms;
-        if (h->ev_kind[k] == 1) *contract += ms;
-        if (h->ev_kind[k] == 2) *chain += ms;
-        if (h->ev_kind[k] == 3) *llmse += ms;
+        const int kind = h->ev_kind[k];
+        if (kind == 4) { in_elbo = true; continue; }
+        (in_elbo ? elbo : sweep) += ms;
+        if (kind == 1) contract += ms;
+        if (kind == 2) chain += ms;
+        if (kind == 3) llmse += ms;
     }
     h->ev_used = 0;
-    return span;
+    h->sweep_ms = sweep; h->elbo_ms = elbo; h->contract_ms = contract; h->chain_ms = chain; h->llmse_ms = llmse;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -449,16 +455,8 @@ int tame_sweep(tame_handle* h) {
             ev_mark(h, 0);
         }
     }
-    CK(cudaMemcpyAsync(h->abort_pinned, h->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ev_mark(h, 4);   // end of the sweep; folded at the next synchronisation (tame_elbo_mse)
     CK(cudaGetLastError());
-    if (h->timing) {
-        CK(cudaStreamSynchronize(st));
-        double c = 0, ch = 0, l = 0;
-        h->sweep_ms = ev_fold(h, &c, &ch, &l);
-        h->contract_ms = c;
-        h->chain_ms = ch;
-        return check_abort(h);
-    }
     return TAME_OK;
 }
 
@@ -485,11 +483,7 @@ int tame_elbo_mse(tame_handle* h, double* out6_host) {
     CK(cudaMemcpyAsync(h->abort_pinned, h->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    if (h->timing) {
-        double c = 0, ch = 0, l = 0;
-        h->elbo_ms = ev_fold(h, &c, &ch, &l);
-        h->llmse_ms = l;
-    }
+    if (h->timing) ev_fold(h);
     memcpy(out6_host, h->out6_pinned, sizeof(double) * 6);
     return check_abort(h);
 }

@@ -124,18 +124,52 @@ __global__ void k_totals_final(TameParams P, const double* partial, int NS) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// asynchronous-copy helpers (LDGSTS): 16-byte global -> shared copies, zero-filled when !valid
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tame_cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void tame_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tame_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// shared-memory stride (doubles) of one staged X_mean record: D, or D+2 when D/2 is even, so that the 8 lanes of
+// a quarter-warp reading 16-byte pieces of consecutive records hit distinct bank groups
+template <int D>
+struct TameRec {
+    static constexpr int RS = ((D / 2) % 2) ? D : D + 2;
+};
+
+// Streaming tile shared by k_contract and k_llmse.
+//   CTA = 8 warps; lane <-> time step t (32 consecutive t: 512 contiguous bytes of Y per partner), warp <-> RW rows.
+//   Y goes global -> shared through a per-thread ring of PD partners (cp.async, RW*PD 16-byte copies in flight
+//   per thread, 128 KB per CTA at RW=4): every thread later reads back exactly the dyads it copied, so the ring
+//   needs no block-level synchronisation.  The partners' X_mean records (a,b,U,V at the CTA's 32 time steps) are
+//   staged in their natural layout, JC partners per chunk, double buffered, one __syncthreads per chunk.
+template <int R, int RW>
+struct TameStream {
+    static constexpr int D = 2 + 2 * R, JC = 8, PD = 8, RS = TameRec<D>::RS, PIECES = D / 2;
+    static constexpr size_t Y_BYTES = (size_t)PD * RW * 256 * sizeof(double2);
+    static constexpr size_t M_BYTES = (size_t)2 * JC * 32 * RS * sizeof(double);
+    static constexpr size_t SMEM = Y_BYTES + M_BYTES;
+};
+
+// ------------------------------------------------------------------------------------------------------
 // k_contract: H[k,t,:] (+)= sum_{j in [j0,j1), (tri ? j>k : j!=k)} ( w0(k,j,t) * V_j(t) , w1(k,j,t) * U_j(t) )
 // with w0 = p0*y0 + q*y1, w1 = q*y0 + p1*y1  -- the [U,V] rows of sum_j J'R^-1 y_ij (structured_mf.py:324).
-// One pass over Y[k0:k1, j0:j1].  lane <-> t (512 contiguous bytes of Y per partner), RW rows per warp,
-// partner vectors staged in shared memory per chunk of JC partners and shared by the CTA's 8*RW rows.
-// grid (ceil(T/32), ceil((k1-k0)/(8*RW))), block 256.
+// One pass over Y[k0:k1, j0:j1].  grid (ceil(T/32), ceil((k1-k0)/(8*RW))), block 256, TameStream::SMEM dynamic smem.
 // ------------------------------------------------------------------------------------------------------
 template <int R, int RW>
-__global__ void __launch_bounds__(256) k_contract(TameParams P, int k0, int k1, int j0, int j1, int tri, int accumulate) {
-    constexpr int D = 2 + 2 * R, NV = 2 * R, JC = 8, RT = 8 * RW;
+__global__ void __launch_bounds__(256, 1) k_contract(TameParams P, int k0, int k1, int j0, int j1, int tri, int accumulate) {
+    using TS = TameStream<R, RW>;
+    constexpr int D = TS::D, NV = 2 * R, JC = TS::JC, PD = TS::PD, RS = TS::RS, RT = 8 * RW;
+    static_assert(JC == PD, "ring slot == position in chunk");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*Ms)[JC][NV][32] = reinterpret_cast<double (*)[JC][NV][32]>(smem_raw);   // [2][JC][NV][32]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2 (*Yr)[RW][256] = reinterpret_cast<double2 (*)[RW][256]>(smem_raw);                       // [PD][RW][256]
+    double (*Mb)[JC][32][RS] = reinterpret_cast<double (*)[JC][32][RS]>(smem_raw + TS::Y_BYTES);     // [2][JC][32][RS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = blockIdx.x * 32, t = t0 + lane;
     const bool tv = t < P.T;
     const int kbase = k0 + blockIdx.y * RT;
@@ -152,60 +186,76 @@ __global__ void __launch_bounds__(256) k_contract(TameParams P, int k0, int k1, 
     bool rv[RW];
 #pragma unroll
     for (int rr = 0; rr < RW; ++rr) {
-        int k = kw + rr;
+        const int k = kw + rr;
         rv[rr] = (k < k1) && tv;
-        int l = tame_lrow(min(k, P.n - 1), P.panel, P.world);
+        const int l = tame_lrow(min(k, P.n - 1), P.panel, P.world);
         yrow[rr] = P.Y + ((size_t)l * P.n * P.T + (tv ? t : 0)) * 2;
     }
     const size_t jstride = (size_t)P.T * 2;
-
-    int jstart = j0;
-    if (tri) jstart = max(j0, ((kbase + 1) / JC) * JC);
+    const int jstart = tri ? max(j0, ((kbase + 1) / JC) * JC) : j0;
     const int nchunks = (j1 > jstart) ? (j1 - jstart + JC - 1) / JC : 0;
 
-    auto stage = [&](int buf, int jc) {
-        // 4096/NV.. elements: (jj, x, tl); thread -> tl = e%32 (coalesced smem), x, jj
-        for (int e = threadIdx.x; e < JC * NV * 32; e += 256) {
-            int tl = e & 31, x = (e >> 5) % NV, jj = (e >> 5) / NV;
-            int j = jc + jj, tt = t0 + tl;
-            double v = 0.0;
-            if (j < j1 && tt < P.T) v = P.Xm[((size_t)j * P.T + tt) * D + tame_zidx<R>(x)];
-            Ms[buf][jj][x][tl] = v;
+    auto issue_y = [&](int j, int slot) {
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr) {
+            const int k = kw + rr;
+            const bool ok = rv[rr] && (j < j1) && (tri ? (j > k) : (j != k));
+            tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
+        }
+    };
+    auto issue_m = [&](int buf, int jc) {
+        for (int e = tid; e < JC * 32 * TS::PIECES; e += 256) {
+            const int piece = e % TS::PIECES, tl = (e / TS::PIECES) & 31, jj = e / (TS::PIECES * 32);
+            const int j = jc + jj, tt = t0 + tl;
+            const bool ok = (j < j1) && (tt < P.T);
+            const double* src = P.Xm + ((size_t)min(j, P.n - 1) * P.T + min(tt, P.T - 1)) * D + piece * 2;
+            tame_cp_async16(&Mb[buf][jj][tl][piece * 2], src, ok);
         }
     };
 
-    if (nchunks > 0) stage(0, jstart);
-    __syncthreads();
+    if (nchunks > 0) {
+        issue_m(0, jstart);
+#pragma unroll
+        for (int s = 0; s < PD; ++s) {
+            issue_y(jstart + s, s);
+            tame_cp_async_commit();
+        }
+    }
     for (int c = 0; c < nchunks; ++c) {
         const int jc = jstart + c * JC, buf = c & 1;
-        if (c + 1 < nchunks) stage(buf ^ 1, jc + JC);
 #pragma unroll
         for (int jj = 0; jj < JC; ++jj) {
+            tame_cp_async_wait<PD - 1>();
+            if (jj == 0) {
+                __syncthreads();                               // chunk c's partner records are visible to the CTA
+                if (c + 1 < nchunks) issue_m(buf ^ 1, jc + JC);
+            }
             double w0[RW], w1[RW];
 #pragma unroll
             for (int rr = 0; rr < RW; ++rr) {
-                const int j = jc + jj, k = kw + rr;
-                const bool ok = rv[rr] && (j < j1) && (tri ? (j > k) : (j != k));
-                const double2 y = ok ? tame_ld_stream2(yrow[rr] + (size_t)j * jstride) : make_double2(0.0, 0.0);
+                const double2 y = Yr[jj][rr][tid];
                 w0[rr] = P.p0 * y.x + P.q * y.y;
                 w1[rr] = P.q * y.x + P.p1 * y.y;
             }
+            const double* rec = &Mb[buf][jj][lane][0];
 #pragma unroll
             for (int a = 0; a < R; ++a) {
-                double zv = Ms[buf][jj][a][lane];       // V_j[a]
-                double zu = Ms[buf][jj][R + a][lane];   // U_j[a]
+                const double zu = rec[2 + a];        // U_j[a]
+                const double zv = rec[2 + R + a];    // V_j[a]
 #pragma unroll
                 for (int rr = 0; rr < RW; ++rr) {
                     accA[rr][a] = fma(w0[rr], zv, accA[rr][a]);
                     accB[rr][a] = fma(w1[rr], zu, accB[rr][a]);
                 }
             }
+            issue_y(jc + jj + PD, jj);
+            tame_cp_async_commit();
         }
-        __syncthreads();
     }
+    tame_cp_async_wait<0>();
 #pragma unroll
     for (int rr = 0; rr < RW; ++rr) {
-        int k = kw + rr;
+        const int k = kw + rr;
         if (k < k1 && tv) {
             double* h = P.H + ((size_t)tame_lrow(k, P.panel, P.world) * P.T + t) * NV;
 #pragma unroll
@@ -530,16 +580,18 @@ __global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int
 //   e0 = y0 - (a_i + b_j + U_i.V_j), e1 = y1 - (a_j + b_i + U_j.V_i)        static_ame.py:226-236
 //   sq   += e0^2 + e1^2                        for all i != j               temporal_ame.py:284-290
 //   quad += p0 e0^2 + 2 q e0 e1 + p1 e1^2      for i < j only               structured_mf.py:136-139
-// Same tiling as k_contract (lane <-> t, RW rows per warp, partner state staged in shared memory).
-// grid (ceil(T/32), ceil(nloc/(8*RW))), block 256; partial (grid.y*grid.x, 2).
+// Same streaming tile as k_contract (TameStream).  grid (ceil(T/32), ceil(nloc/(8*RW))), block 256;
+// partial (grid.y*grid.x, 2).
 // ------------------------------------------------------------------------------------------------------
 template <int R, int RW>
-__global__ void __launch_bounds__(256) k_llmse(TameParams P, double* partial) {
-    constexpr int D = 2 + 2 * R, JC = 8, RT = 8 * RW;
+__global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial) {
+    using TS = TameStream<R, RW>;
+    constexpr int D = TS::D, JC = TS::JC, PD = TS::PD, RS = TS::RS, RT = 8 * RW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*Xs)[JC][D][32] = reinterpret_cast<double (*)[JC][D][32]>(smem_raw);     // [2][JC][D][32]
+    double2 (*Yr)[RW][256] = reinterpret_cast<double2 (*)[RW][256]>(smem_raw);
+    double (*Mb)[JC][32][RS] = reinterpret_cast<double (*)[JC][32][RS]>(smem_raw + TS::Y_BYTES);
     __shared__ double red[2][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = blockIdx.x * 32, t = t0 + lane;
     const bool tv = t < P.T;
     const int lw = blockIdx.y * RT + warp * RW;
@@ -564,37 +616,47 @@ __global__ void __launch_bounds__(256) k_llmse(TameParams P, double* partial) {
     const size_t jstride = (size_t)P.T * 2;
     double sq = 0.0, quad = 0.0;
 
-    auto stage = [&](int buf, int jc) {
-        for (int e = threadIdx.x; e < JC * D * 32; e += 256) {
-            int tl = e & 31, k = (e >> 5) % D, jj = (e >> 5) / D;
-            int j = jc + jj, tt = t0 + tl;
-            double v = 0.0;
-            if (j < P.n && tt < P.T) v = P.Xm[((size_t)j * P.T + tt) * D + k];
-            Xs[buf][jj][k][tl] = v;
+    auto issue_y = [&](int j, int slot) {
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr) {
+            const bool ok = rv[rr] && (j < P.n) && (j != gi[rr]);
+            tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
+        }
+    };
+    auto issue_m = [&](int buf, int jc) {
+        for (int e = tid; e < JC * 32 * TS::PIECES; e += 256) {
+            const int piece = e % TS::PIECES, tl = (e / TS::PIECES) & 31, jj = e / (TS::PIECES * 32);
+            const int j = jc + jj, tt = t0 + tl;
+            const bool ok = (j < P.n) && (tt < P.T);
+            const double* src = P.Xm + ((size_t)min(j, P.n - 1) * P.T + min(tt, P.T - 1)) * D + piece * 2;
+            tame_cp_async16(&Mb[buf][jj][tl][piece * 2], src, ok);
         }
     };
     const int nchunks = (P.n + JC - 1) / JC;
-    stage(0, 0);
-    __syncthreads();
+    issue_m(0, 0);
+#pragma unroll
+    for (int s = 0; s < PD; ++s) {
+        issue_y(s, s);
+        tame_cp_async_commit();
+    }
     for (int c = 0; c < nchunks; ++c) {
         const int jc = c * JC, buf = c & 1;
-        if (c + 1 < nchunks) stage(buf ^ 1, jc + JC);
 #pragma unroll
         for (int jj = 0; jj < JC; ++jj) {
             const int j = jc + jj;
-            double2 y[RW];
-#pragma unroll
-            for (int rr = 0; rr < RW; ++rr) {
-                const bool ok = rv[rr] && (j < P.n) && (j != gi[rr]);
-                y[rr] = ok ? tame_ld_stream2(yrow[rr] + (size_t)j * jstride) : make_double2(0.0, 0.0);
+            tame_cp_async_wait<PD - 1>();
+            if (jj == 0) {
+                __syncthreads();
+                if (c + 1 < nchunks) issue_m(buf ^ 1, jc + JC);
             }
-            const double aj = Xs[buf][jj][0][lane], bj = Xs[buf][jj][1][lane];
+            const double* rec = &Mb[buf][jj][lane][0];
+            const double aj = rec[0], bj = rec[1];
             double d0[RW], d1[RW];
 #pragma unroll
             for (int rr = 0; rr < RW; ++rr) { d0[rr] = 0.0; d1[rr] = 0.0; }
 #pragma unroll
             for (int a = 0; a < R; ++a) {
-                const double uj = Xs[buf][jj][2 + a][lane], vj = Xs[buf][jj][2 + R + a][lane];
+                const double uj = rec[2 + a], vj = rec[2 + R + a];
 #pragma unroll
                 for (int rr = 0; rr < RW; ++rr) {
                     d0[rr] = fma(oU[rr][a], vj, d0[rr]);
@@ -603,17 +665,20 @@ __global__ void __launch_bounds__(256) k_llmse(TameParams P, double* partial) {
             }
 #pragma unroll
             for (int rr = 0; rr < RW; ++rr) {
+                const double2 y = Yr[jj][rr][tid];
                 const bool ok = rv[rr] && (j < P.n) && (j != gi[rr]);
                 if (ok) {
-                    const double e0 = y[rr].x - ((oa[rr] + bj) + d0[rr]);
-                    const double e1 = y[rr].y - ((aj + ob[rr]) + d1[rr]);
+                    const double e0 = y.x - ((oa[rr] + bj) + d0[rr]);
+                    const double e1 = y.y - ((aj + ob[rr]) + d1[rr]);
                     sq += e0 * e0 + e1 * e1;
                     if (j > gi[rr]) quad += P.p0 * e0 * e0 + 2.0 * P.q * e0 * e1 + P.p1 * e1 * e1;
                 }
             }
+            issue_y(j + PD, jj);
+            tame_cp_async_commit();
         }
-        __syncthreads();
     }
+    tame_cp_async_wait<0>();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sq += __shfl_xor_sync(0xffffffffu, sq, o);

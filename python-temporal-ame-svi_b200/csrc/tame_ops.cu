@@ -19,7 +19,7 @@ void launch_totals(const TameParams& P, double* partial, int NS, cudaStream_t st
 void launch_contract(const TameParams& P, int k0, int k1, int j0, int j1, int tri, int accumulate, cudaStream_t st) {
     if (k1 <= k0 || j1 <= j0) return;
     dim3 grid((P.T + 31) / 32, (k1 - k0 + 8 * RW - 1) / (8 * RW));
-    constexpr size_t smem = 2 * 8 * (2 * R) * 32 * sizeof(double);
+    constexpr size_t smem = TameStream<R, RW>::SMEM;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_contract<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -59,7 +59,7 @@ int llmse_blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 8 
 
 void launch_llmse(const TameParams& P, double* partial, int* nblocks, cudaStream_t st) {
     dim3 grid((P.T + 31) / 32, (P.nloc + 8 * RW - 1) / (8 * RW));
-    constexpr size_t smem = 2 * 8 * (2 + 2 * R) * 32 * sizeof(double);
+    constexpr size_t smem = TameStream<R, RW>::SMEM;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_llmse<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
