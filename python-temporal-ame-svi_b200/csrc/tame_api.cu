@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,7 +101,9 @@ struct tame_handle {
     // device scratch
     double *H = nullptr, *hab = nullptr, *tot = nullptr, *tot_partial = nullptr, *cst = nullptr;
     double *part_ll = nullptr, *part_cell = nullptr, *red6 = nullptr, *out6 = nullptr;
-    int *progress = nullptr, *abort_flag = nullptr;
+    int *progress = nullptr, *abort_flag = nullptr, *unit_counter = nullptr, *unit_done = nullptr;
+    int epoch = 0;
+    bool fused = true;
     int NS = 1, nb_ll = 0, nb_cell = 0;
     double* out6_pinned = nullptr;
     int* abort_pinned = nullptr;
@@ -337,6 +340,9 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     if (e == cudaSuccess) e = dalloc((void**)&h->tot_partial, sizeof(double) * (size_t)T * h->NS * TOT);
     if (e == cudaSuccess) e = dalloc((void**)&h->progress, sizeof(int) * T);
     if (e == cudaSuccess) e = dalloc((void**)&h->abort_flag, sizeof(int));
+    const size_t nunits = (size_t)((n + TAME_SB - 1) / TAME_SB) * ((T + 31) / 32);
+    if (e == cudaSuccess) e = dalloc((void**)&h->unit_counter, sizeof(int));
+    if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits);
     if (e == cudaSuccess) e = dalloc((void**)&h->red6, sizeof(double) * 6);
     if (e == cudaSuccess) e = dalloc((void**)&h->out6, sizeof(double) * 6);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out6_pinned, sizeof(double) * 6);
@@ -345,12 +351,20 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     CK(cudaMemcpy(h->cst, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice));
     CK(cudaMemset(h->progress, 0, sizeof(int) * T));
     CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
+    CK(cudaMemset(h->unit_counter, 0, sizeof(int)));
+    CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits));
+    {
+        const char* v = getenv("TAME_SWEEP");   // "panel" forces the stream-ordered per-panel path (debug / comparison)
+        h->fused = (world == 1) && !(v && strcmp(v, "panel") == 0);
+        if (h->fused && (T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC + 1 > h->ops->sweep_capacity()) h->fused = false;
+    }
 
     TameParams& P = h->P;
     P.n = n; P.T = T; P.nloc = nloc; P.world = world; P.rank = rank; P.panel = panel; P.mode = cfg->mode;
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
+    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0;
 
     h->nb_ll = h->ops->llmse_blocks(P);
     h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
@@ -366,7 +380,8 @@ int tame_destroy(tame_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : {(void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
-                    (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag})
+                    (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
+                    (void*)h->unit_counter, (void*)h->unit_done})
         if (p) cudaFree(p);
     if (h->out6_pinned) cudaFreeHost(h->out6_pinned);
     if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
@@ -429,30 +444,39 @@ int tame_sweep(tame_handle* h) {
     // running totals of the partner moments from the current means; resets the progress counters
     ops->totals(P, h->tot_partial, h->NS, st);
     ev_mark(h, 1);
-    // static upper part: partners j > k still carry their old means when row k is updated
-    ops->contract(P, 0, n, 0, n, /*tri=*/1, /*accumulate=*/0, st);
-    ev_mark(h, 0);
-    for (int lo = 0; lo < n; lo += TAME_WIN) {
-        const int hi = std::min(n, lo + TAME_WIN);
-        const int owner = (lo / h->panel) % world;
-        if (owner == rank) {
-            ev_mark(h, 2);
-            cudaError_t e = ops->chain(P, lo, hi, st);
-            if (e != cudaSuccess) return fail(TAME_ECUDA, "chain launch: %s", cudaGetErrorString(e));
-            ev_mark(h, 0);
-        }
-        if (world > 1) {
-            if (!h->comm) return fail(TAME_ESTATE, "world > 1 but tame_comm_init was not called");
-            NK(g_nccl.GroupStart());
-            NK(g_nccl.Broadcast(P.Xm + (size_t)lo * T * d, P.Xm + (size_t)lo * T * d, (size_t)(hi - lo) * T * d, ncclDouble, owner, h->comm, st));
-            NK(g_nccl.Broadcast(P.tot, P.tot, (size_t)T * ops->tot, ncclDouble, owner, h->comm, st));
-            NK(g_nccl.GroupEnd());
-        }
-        if (hi < n) {
-            // right-looking push: the block's new means reach every later row
-            ev_mark(h, 1);
-            ops->contract(P, hi, n, lo, hi, /*tri=*/0, /*accumulate=*/1, st);
-            ev_mark(h, 0);
+    if (h->fused) {
+        // single GPU: the whole sweep is one persistent cooperative launch (chain CTAs + streaming CTAs)
+        h->P.epoch = ++h->epoch;
+        ev_mark(h, 2);
+        cudaError_t e = ops->sweep_fused(h->P, st);
+        if (e != cudaSuccess) return fail(TAME_ECUDA, "fused sweep launch: %s", cudaGetErrorString(e));
+        ev_mark(h, 0);
+    } else {
+        // static upper part: partners j > k still carry their old means when row k is updated
+        ops->contract(P, 0, n, 0, n, /*tri=*/1, /*accumulate=*/0, st);
+        ev_mark(h, 0);
+        for (int lo = 0; lo < n; lo += TAME_WIN) {
+            const int hi = std::min(n, lo + TAME_WIN);
+            const int owner = (lo / h->panel) % world;
+            if (owner == rank) {
+                ev_mark(h, 2);
+                cudaError_t e = ops->chain(P, lo, hi, st);
+                if (e != cudaSuccess) return fail(TAME_ECUDA, "chain launch: %s", cudaGetErrorString(e));
+                ev_mark(h, 0);
+            }
+            if (world > 1) {
+                if (!h->comm) return fail(TAME_ESTATE, "world > 1 but tame_comm_init was not called");
+                NK(g_nccl.GroupStart());
+                NK(g_nccl.Broadcast(P.Xm + (size_t)lo * T * d, P.Xm + (size_t)lo * T * d, (size_t)(hi - lo) * T * d, ncclDouble, owner, h->comm, st));
+                NK(g_nccl.Broadcast(P.tot, P.tot, (size_t)T * ops->tot, ncclDouble, owner, h->comm, st));
+                NK(g_nccl.GroupEnd());
+            }
+            if (hi < n) {
+                // right-looking push: the block's new means reach every later row
+                ev_mark(h, 1);
+                ops->contract(P, hi, n, lo, hi, /*tri=*/0, /*accumulate=*/1, st);
+                ev_mark(h, 0);
+            }
         }
     }
     ev_mark(h, 4);   // end of the sweep; folded at the next synchronisation (tame_elbo_mse)

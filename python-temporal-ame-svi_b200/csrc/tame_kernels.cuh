@@ -27,6 +27,7 @@
 #define TAME_WIN 64          // inline window of the chain kernel (nodes)
 #define TAME_CHAIN_WPC 8     // warps (time steps) per chain CTA
 #define TAME_SPIN_LIMIT (1 << 24)
+#define TAME_SB 32           // sub-block of the fused sweep: rows per streaming unit, push granularity
 
 struct TameParams {
     int n, T, nloc, world, rank, panel, mode;
@@ -40,6 +41,11 @@ struct TameParams {
     const double* cst;        // 6 DxD matrices: S0inv, Qinv, Phi'QinvPhi, QinvPhi, Phi'Qinv, Phi
     int* progress;            // (T) nodes finished in this sweep by the warp of time t
     int* abort_flag;
+    // fused sweep (k_sweep): work distribution between the chain CTAs and the streaming CTAs
+    int* unit_counter;        // next (sub-block, t-slice) unit to hand to a streaming CTA
+    int* unit_done;           // (nsb * nslices) epoch stamp written when a unit's H rows are complete
+    int epoch;                // sweep number (stamps are compared against it; never reset)
+    int n_chain_ctas;
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -120,7 +126,10 @@ __global__ void k_totals_final(TameParams P, const double* partial, int NS) {
         for (int s = 0; s < NS; ++s) acc += partial[((size_t)t * NS + s) * TOT + e];
         P.tot[(size_t)t * TOT + e] = acc;
     }
-    if (threadIdx.x == 0) P.progress[t] = 0;
+    if (threadIdx.x == 0) {
+        P.progress[t] = 0;
+        if (t == 0) *P.unit_counter = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -157,49 +166,30 @@ struct TameStream {
 };
 
 // ------------------------------------------------------------------------------------------------------
-// k_contract: H[k,t,:] (+)= sum_{j in [j0,j1), (tri ? j>k : j!=k)} ( w0(k,j,t) * V_j(t) , w1(k,j,t) * U_j(t) )
-// with w0 = p0*y0 + q*y1, w1 = q*y0 + p1*y1  -- the [U,V] rows of sum_j J'R^-1 y_ij (structured_mf.py:324).
-// One pass over Y[k0:k1, j0:j1].  grid (ceil(T/32), ceil((k1-k0)/(8*RW))), block 256, TameStream::SMEM dynamic smem.
+// tame_stream_cols: acc += sum_{j in [jb,je), (tri ? j>k : j!=k)} ( w0(k,j,t) * V_j(t) , w1(k,j,t) * U_j(t) )
+// for the CTA's 8*RW rows (warp <-> RW rows starting at kw) and 32 time steps (lane <-> t), with
+// w0 = p0*y0 + q*y1, w1 = q*y0 + p1*y1  -- the [U,V] rows of sum_j J'R^-1 y_ij (structured_mf.py:324).
+// Software pipeline described at TameStream.  Must be called by all 256 threads of the CTA.
 // ------------------------------------------------------------------------------------------------------
 template <int R, int RW>
-__global__ void __launch_bounds__(256, 1) k_contract(TameParams P, int k0, int k1, int j0, int j1, int tri, int accumulate) {
+__device__ __forceinline__ void tame_stream_cols(const TameParams& P, unsigned char* smem_raw, const double* const (&yrow)[RW],
+                                                 const bool (&rv)[RW], int kw, int t0, int jb, int je, bool tri,
+                                                 double (&accA)[RW][R], double (&accB)[RW][R]) {
     using TS = TameStream<R, RW>;
-    constexpr int D = TS::D, NV = 2 * R, JC = TS::JC, PD = TS::PD, RS = TS::RS, RT = 8 * RW;
+    constexpr int D = TS::D, JC = TS::JC, PD = TS::PD, RS = TS::RS;
     static_assert(JC == PD, "ring slot == position in chunk");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 (*Yr)[RW][256] = reinterpret_cast<double2 (*)[RW][256]>(smem_raw);                       // [PD][RW][256]
     double (*Mb)[JC][32][RS] = reinterpret_cast<double (*)[JC][32][RS]>(smem_raw + TS::Y_BYTES);     // [2][JC][32][RS]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t0 = blockIdx.x * 32, t = t0 + lane;
-    const bool tv = t < P.T;
-    const int kbase = k0 + blockIdx.y * RT;
-    if (!tame_owned(kbase, P.panel, P.world, P.rank)) return;   // RT divides the panel size
-    const int kw = kbase + warp * RW;
-
-    double accA[RW][R], accB[RW][R];
-#pragma unroll
-    for (int rr = 0; rr < RW; ++rr)
-#pragma unroll
-        for (int a = 0; a < R; ++a) accA[rr][a] = accB[rr][a] = 0.0;
-
-    const double* yrow[RW];
-    bool rv[RW];
-#pragma unroll
-    for (int rr = 0; rr < RW; ++rr) {
-        const int k = kw + rr;
-        rv[rr] = (k < k1) && tv;
-        const int l = tame_lrow(min(k, P.n - 1), P.panel, P.world);
-        yrow[rr] = P.Y + ((size_t)l * P.n * P.T + (tv ? t : 0)) * 2;
-    }
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t jstride = (size_t)P.T * 2;
-    const int jstart = tri ? max(j0, ((kbase + 1) / JC) * JC) : j0;
-    const int nchunks = (j1 > jstart) ? (j1 - jstart + JC - 1) / JC : 0;
+    const int nchunks = (je > jb) ? (je - jb + JC - 1) / JC : 0;
+    if (nchunks == 0) return;
 
     auto issue_y = [&](int j, int slot) {
 #pragma unroll
         for (int rr = 0; rr < RW; ++rr) {
             const int k = kw + rr;
-            const bool ok = rv[rr] && (j < j1) && (tri ? (j > k) : (j != k));
+            const bool ok = rv[rr] && (j < je) && (tri ? (j > k) : (j != k));
             tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
         }
     };
@@ -207,22 +197,21 @@ __global__ void __launch_bounds__(256, 1) k_contract(TameParams P, int k0, int k
         for (int e = tid; e < JC * 32 * TS::PIECES; e += 256) {
             const int piece = e % TS::PIECES, tl = (e / TS::PIECES) & 31, jj = e / (TS::PIECES * 32);
             const int j = jc + jj, tt = t0 + tl;
-            const bool ok = (j < j1) && (tt < P.T);
+            const bool ok = (j < je) && (tt < P.T);
             const double* src = P.Xm + ((size_t)min(j, P.n - 1) * P.T + min(tt, P.T - 1)) * D + piece * 2;
             tame_cp_async16(&Mb[buf][jj][tl][piece * 2], src, ok);
         }
     };
 
-    if (nchunks > 0) {
-        issue_m(0, jstart);
+    __syncthreads();            // the staging buffers may still be read by a previous call
+    issue_m(0, jb);
 #pragma unroll
-        for (int s = 0; s < PD; ++s) {
-            issue_y(jstart + s, s);
-            tame_cp_async_commit();
-        }
+    for (int s = 0; s < PD; ++s) {
+        issue_y(jb + s, s);
+        tame_cp_async_commit();
     }
     for (int c = 0; c < nchunks; ++c) {
-        const int jc = jstart + c * JC, buf = c & 1;
+        const int jc = jb + c * JC, buf = c & 1;
 #pragma unroll
         for (int jj = 0; jj < JC; ++jj) {
             tame_cp_async_wait<PD - 1>();
@@ -253,6 +242,40 @@ __global__ void __launch_bounds__(256, 1) k_contract(TameParams P, int k0, int k
         }
     }
     tame_cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_contract: H[k,t,:] (+)= contraction over partners j in [j0,j1) for rows [k0,k1) (stand-alone launches: the
+// multi-GPU sweep's static upper part and right-looking pushes).  One pass over Y[k0:k1, j0:j1].
+// grid (ceil(T/32), ceil((k1-k0)/(8*RW))), block 256, TameStream::SMEM dynamic smem.
+// ------------------------------------------------------------------------------------------------------
+template <int R, int RW>
+__global__ void __launch_bounds__(256, 1) k_contract(TameParams P, int k0, int k1, int j0, int j1, int tri, int accumulate) {
+    constexpr int NV = 2 * R, JC = TameStream<R, RW>::JC, RT = 8 * RW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = blockIdx.x * 32, t = t0 + lane;
+    const bool tv = t < P.T;
+    const int kbase = k0 + blockIdx.y * RT;
+    if (!tame_owned(kbase, P.panel, P.world, P.rank)) return;   // RT divides the panel size
+    const int kw = kbase + warp * RW;
+
+    double accA[RW][R], accB[RW][R];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr)
+#pragma unroll
+        for (int a = 0; a < R; ++a) accA[rr][a] = accB[rr][a] = 0.0;
+    const double* yrow[RW];
+    bool rv[RW];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+        const int k = kw + rr;
+        rv[rr] = (k < k1) && tv;
+        const int l = tame_lrow(min(k, P.n - 1), P.panel, P.world);
+        yrow[rr] = P.Y + ((size_t)l * P.n * P.T + (tv ? t : 0)) * 2;
+    }
+    const int jstart = tri ? max(j0, ((kbase + 1) / JC) * JC) : j0;
+    tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, jstart, j1, tri != 0, accA, accB);
 #pragma unroll
     for (int rr = 0; rr < RW; ++rr) {
         const int k = kw + rr;
@@ -345,18 +368,20 @@ __device__ __forceinline__ void tame_tot_update(double* tot, const double* m, do
 //   4. writes the damped mean/covariance (:282-287), publishes progress, restores the totals with the new mean.
 // Launched cooperatively (all CTAs co-resident): warps spin on their predecessor's progress counter.
 // ------------------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int i0, int i1) {
+template <int R, bool FUSED>
+__device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned char* smem_raw, int cta, int i0, int i1) {
     using S = TameChainSmem<R>;
+    // inline window: FUSED  -> previous + current 32-node sub-block (the streaming CTAs cover everything older),
+    //                !FUSED -> the current 64-node block only (earlier blocks were pushed by k_contract launches)
+    constexpr int WSB = FUSED ? TAME_SB : TAME_WIN;
     constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP, NE = (D * D + 31) / 32, NWS = TAME_WIN / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     double* cstQP = reinterpret_cast<double*>(smem_raw);          // QinvPhi   (D*D)
     double* cstPQ = cstQP + D * D;                                // Phi'Qinv  (D*D)
     S* warps = reinterpret_cast<S*>(cstPQ + D * D);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < 2 * D * D; e += blockDim.x) cstQP[e] = P.cst[3 * D * D + e];
     __syncthreads();
-    const int t = blockIdx.x * TAME_CHAIN_WPC + warp;
+    const int t = cta * TAME_CHAIN_WPC + warp;
     if (t >= P.T) return;
     S& sm = warps[warp];
     const int T = P.T;
@@ -385,15 +410,19 @@ __global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int
     const double lr = P.lr, om = 1.0 - P.lr;
     __syncwarp();
 
+    auto window_lo = [&](int i) { return FUSED ? max(0, (i / WSB - 1) * WSB) : (i / WSB) * WSB; };
+    const int nslices = (T + 31) / 32;
+
     // prefetch registers for node i
     double2 yv[NWS];
     double cold[NE];
-    double hbase = 0.0, mold = 0.0, mnext = 0.0;
+    double mold = 0.0, mnext = 0.0;
     auto prefetch = [&](int i) {
         const int l = tame_lrow(i, P.panel, P.world);
+        const int wlo = window_lo(i);
 #pragma unroll
         for (int s = 0; s < NWS; ++s) {
-            int j = i0 + lane + 32 * s;
+            int j = wlo + lane + 32 * s;
             yv[s] = (j < i) ? tame_ld_stream2(P.Y + (((size_t)l * P.n + j) * T + t) * 2) : make_double2(0.0, 0.0);
         }
         const double* cp = P.Xc + ((size_t)i * T + t) * D * D;
@@ -402,8 +431,6 @@ __global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int
             int e = lane + 32 * m;
             cold[m] = (e < D * D) ? __ldcs(cp + e) : 0.0;
         }
-        if (c < 2) hbase = P.hab[((size_t)l * T + t) * 2 + c];
-        else if (c < D) hbase = __ldcg(P.H + ((size_t)l * T + t) * NV + (c - 2));
         if (c < D) {
             mold = tame_ld_cg(P.Xm + ((size_t)i * T + t) * D + c);
             mnext = has_next ? tame_ld_cg(P.Xm + ((size_t)i * T + t + 1) * D + c) : 0.0;
@@ -419,8 +446,27 @@ __global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int
         double ccur[NE];
 #pragma unroll
         for (int m = 0; m < NE; ++m) ccur[m] = cold[m];
-        const double hb = hbase, mo = mold, mn = mnext;
+        const double mo = mold, mn = mnext;
         if (i + 1 < i1) prefetch(i + 1);
+        if (FUSED && (i % TAME_SB) == 0) {
+            // the static partner part H of this sub-block comes from a streaming CTA of the same launch
+            if (lane == 0) {
+                const int* flag = P.unit_done + (i / TAME_SB) * nslices + (t >> 5);
+                int spins = 0;
+                while (tame_ld_acquire(flag) != P.epoch) {
+                    if (++spins > TAME_SPIN_LIMIT) { atomicExch(P.abort_flag, 1); break; }
+                    if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+                }
+            }
+            __syncwarp();
+        }
+        double hb = 0.0;
+        {
+            const int l = tame_lrow(i, P.panel, P.world);
+            if (c < 2) hb = P.hab[((size_t)l * T + t) * 2 + c];
+            else if (c < D) hb = __ldcg(P.H + ((size_t)l * T + t) * NV + (c - 2));
+        }
+        const int wlo = window_lo(i);
 
         if (c < D) { sm.mold[c] = mo; sm.mnext[c] = mn; }
         __syncwarp();
@@ -463,12 +509,13 @@ __global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int
                 sm.wbuf[slot * 2 + 1] = P.q * ycur[s].x + P.p1 * ycur[s].y;
             }
             __syncwarp();
-            const int cnt = i - i0;
+            const int cnt = i - wlo;
             const int x = lane & 15, half = lane >> 4;
             double acc = 0.0;
             if (x < NV) {
                 const int wsel = (x < R) ? 0 : 1;
-                for (int jj = half; jj < cnt; jj += 2) acc = fma(sm.wbuf[jj * 2 + wsel], sm.ring[jj][x], acc);
+                for (int jj = half; jj < cnt; jj += 2)
+                    acc = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_WIN - 1)][x], acc);
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             if (lane < NV) sm.hin[lane] = acc;
@@ -569,10 +616,111 @@ __global__ void __launch_bounds__(TAME_CHAIN_WPC * 32) k_chain(TameParams P, int
         }
         // ---- totals with the new mean, window ring
         tame_tot_update<R>(sm.tot, sm.mnew, 1.0, lane);
-        if (lane < NV) sm.ring[i - i0][lane] = tame_zof<R>(sm.mnew, lane);
+        if (lane < NV) sm.ring[i & (TAME_WIN - 1)][lane] = tame_zof<R>(sm.mnew, lane);
         __syncwarp();
     }
     for (int e = lane; e < TOT; e += 32) P.tot[(size_t)t * TOT + e] = sm.tot[e];
+}
+
+
+// stand-alone chain launch over one 64-node block (multi-GPU path); cooperative, grid = ceil(T/8)
+template <int R>
+__global__ void __launch_bounds__(TAME_CHAIN_WPC * 32, 1) k_chain(TameParams P, int i0, int i1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tame_chain_body<R, false>(P, smem_raw, blockIdx.x, i0, i1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_sweep: one whole Gauss-Seidel sweep in ONE persistent cooperative launch (single-GPU path).
+//   CTAs [0, n_chain_ctas)   run the chain over all nodes 0..n-1 (tame_chain_body<FUSED>): no pipeline refill.
+//   the remaining CTAs       are streaming workers.  A unit = (32-row sub-block sb, 32-step time slice).  A worker
+//       takes units in ascending order from an atomic counter, keeps the unit's 32 x 32 x 2R partner sums in
+//       registers, streams  (a) the static upper part j > k (partners still carrying their old means when row k
+//       is updated) immediately and (b) the lower columns j < (sb-1)*32 (new means) as the chain's progress
+//       counters release them, then writes H once (no read-modify-write, no atomics) and stamps unit_done.
+//   The chain waits for a sub-block's stamp before entering it and covers the last (up to) 64 partners inline.
+// Every Y entry is read exactly once per sweep; the schedule is the reference's.
+// grid = n_chain_ctas + workers (all co-resident), block 256, dynamic smem = max of the two roles.
+// ------------------------------------------------------------------------------------------------------
+template <int R, int RW>
+__global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(8 * RW == TAME_SB, "a streaming unit is one sub-block of rows");
+    if ((int)blockIdx.x < P.n_chain_ctas) {
+        tame_chain_body<R, true>(P, smem_raw, blockIdx.x, 0, P.n);
+        return;
+    }
+    constexpr int NV = 2 * R, JC = TameStream<R, RW>::JC;
+    __shared__ int s_val;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nslices = (P.T + 31) / 32, nsb = (P.n + TAME_SB - 1) / TAME_SB, nunits = nsb * nslices;
+    for (;;) {
+        if (tid == 0) s_val = atomicAdd(P.unit_counter, 1);
+        __syncthreads();
+        const int u = s_val;
+        __syncthreads();
+        if (u >= nunits) break;
+        const int sb = u / nslices, slice = u - sb * nslices;
+        const int kbase = sb * TAME_SB, kw = kbase + warp * RW;
+        const int t0 = slice * 32, t = t0 + lane;
+        const bool tv = t < P.T;
+        double accA[RW][R], accB[RW][R];
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr)
+#pragma unroll
+            for (int a = 0; a < R; ++a) accA[rr][a] = accB[rr][a] = 0.0;
+        const double* yrow[RW];
+        bool rv[RW];
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr) {
+            const int k = kw + rr;
+            rv[rr] = (k < P.n) && tv;
+            yrow[rr] = P.Y + ((size_t)min(k, P.n - 1) * P.n * P.T + (tv ? t : 0)) * 2;
+        }
+        // (a) static upper part
+        tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, ((kbase + 1) / JC) * JC, P.n, true, accA, accB);
+        // (b) lower columns, released by the chain
+        const int lowend = max(0, (sb - 1) * TAME_SB);
+        int done_cols = 0, spins = 0;
+        bool dead = false;
+        while (done_cols < lowend && !dead) {
+            if (warp == 0) {
+                int v = (t0 + lane < P.T) ? tame_ld_acquire(P.progress + t0 + lane) : 0x7fffffff;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) {
+                    if (++spins > TAME_SPIN_LIMIT / 8) atomicExch(P.abort_flag, 1);
+                    s_val = *((volatile int*)P.abort_flag) ? -1 : v;
+                }
+            }
+            __syncthreads();
+            const int avail = s_val;
+            __syncthreads();
+            if (avail < 0) { dead = true; break; }
+            const int target = min(lowend, (avail / TAME_SB) * TAME_SB);
+            if (target > done_cols) {
+                tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, done_cols, target, false, accA, accB);
+                done_cols = target;
+            } else {
+                __nanosleep(256);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr) {
+            const int k = kw + rr;
+            if (k < P.n && tv) {
+                double* h = P.H + ((size_t)k * P.T + t) * NV;
+#pragma unroll
+                for (int a = 0; a < R; ++a) {
+                    __stcg(h + a, accA[rr][a]);
+                    __stcg(h + R + a, accB[rr][a]);
+                }
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) tame_st_release(P.unit_done + u, P.epoch);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -799,6 +947,8 @@ struct TameOps {
     void (*totals)(const TameParams&, double* partial, int NS, cudaStream_t);
     void (*contract)(const TameParams&, int k0, int k1, int j0, int j1, int tri, int accumulate, cudaStream_t);
     cudaError_t (*chain)(const TameParams&, int i0, int i1, cudaStream_t);
+    cudaError_t (*sweep_fused)(const TameParams&, cudaStream_t);
+    int (*sweep_capacity)();
     int (*chain_max_T)();
     void (*llmse)(const TameParams&, double* partial, int* nblocks, cudaStream_t);
     void (*cellterms)(const TameParams&, double logdetS0, double logdetQ, double* partial, int nblocks, cudaStream_t);

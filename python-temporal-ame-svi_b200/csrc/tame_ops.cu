@@ -46,6 +46,31 @@ cudaError_t launch_chain(const TameParams& P, int i0, int i1, cudaStream_t st) {
     return cudaLaunchCooperativeKernel((void*)k_chain<R>, grid, dim3(TAME_CHAIN_WPC * 32), args, smem, st);
 }
 
+size_t sweep_smem_bytes() { return chain_smem_bytes() > TameStream<R, RW>::SMEM ? chain_smem_bytes() : TameStream<R, RW>::SMEM; }
+
+// co-resident CTAs of k_sweep on the current device
+int sweep_capacity() {
+    int dev = 0, sms = 0, per = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_sweep<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep<R, RW>, 256, sweep_smem_bytes());
+    return sms * per;
+}
+
+cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
+    static int capacity = -1;
+    if (capacity < 0) capacity = sweep_capacity();
+    TameParams p = P;
+    p.n_chain_ctas = (P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC;
+    const int nunits = ((P.n + TAME_SB - 1) / TAME_SB) * ((P.T + 31) / 32);
+    const int workers = capacity - p.n_chain_ctas < nunits ? capacity - p.n_chain_ctas : nunits;
+    if (workers < 1) return cudaErrorLaunchOutOfResources;
+    void* args[] = {(void*)&p};
+    tame_count_launch(1);
+    return cudaLaunchCooperativeKernel((void*)k_sweep<R, RW>, dim3(p.n_chain_ctas + workers), dim3(256), args, sweep_smem_bytes(), st);
+}
+
 int chain_max_T() {
     int dev = 0, sms = 0, per = 0;
     cudaGetDevice(&dev);
@@ -79,5 +104,5 @@ void launch_cellterms(const TameParams& P, double logdetS0, double logdetQ, doub
 #define TAME_CAT2(a, b) a##b
 #define TAME_CAT(a, b) TAME_CAT2(a, b)
 extern const TameOps TAME_CAT(tame_ops_r, TAME_R) = {
-    R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, chain_max_T,
+    R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, launch_sweep_fused, sweep_capacity, chain_max_T,
     launch_llmse, launch_cellterms, llmse_blocks};

@@ -101,9 +101,20 @@ def _random_problem(n, T, r, seed, rho=0.5, ar=0.8):
 SHAPES = [(70, 3, 1), (65, 7, 2), (130, 5, 3), (96, 33, 4), (64, 4, 5), (100, 2, 6), (67, 9, 7), (129, 6, 8), (200, 40, 2)]
 
 
+@pytest.fixture(params=["fused", "panel"])
+def sweep_path(request, monkeypatch):
+    """Both schedulers of the same sweep: the persistent fused kernel (single-GPU default) and the stream-ordered
+    per-panel launches (the multi-GPU path, forced here on one GPU)."""
+    if request.param == "panel":
+        monkeypatch.setenv("TAME_SWEEP", "panel")
+    else:
+        monkeypatch.delenv("TAME_SWEEP", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("meth", METHODS)
 @pytest.mark.parametrize("shape", SHAPES)
-def test_c_abi_matches_oracle_on_seeded_inputs(shape, meth):
+def test_c_abi_matches_oracle_on_seeded_inputs(shape, meth, sweep_path):
     from gpu_util import fit_host
     n, T, r = shape
     c, Y, Xm, Xc = _random_problem(n, T, r, seed=1000 + n + T + r, rho=0.5 if r % 2 else -0.3)
