@@ -104,6 +104,7 @@ struct tame_handle {
     int *progress = nullptr, *abort_flag = nullptr, *unit_counter = nullptr, *unit_done = nullptr;
     int epoch = 0;
     bool fused = true;
+    double2* hand = nullptr;
     int NS = 1, nb_ll = 0, nb_cell = 0;
     double* out6_pinned = nullptr;
     int* abort_pinned = nullptr;
@@ -342,6 +343,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     if (e == cudaSuccess) e = dalloc((void**)&h->abort_flag, sizeof(int));
     const size_t nunits = (size_t)((n + TAME_SB - 1) / TAME_SB) * ((T + 31) / 32);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_counter, sizeof(int));
+    if (e == cudaSuccess) e = dalloc((void**)&h->hand, sizeof(double2) * (size_t)n * T * d);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits);
     if (e == cudaSuccess) e = dalloc((void**)&h->red6, sizeof(double) * 6);
     if (e == cudaSuccess) e = dalloc((void**)&h->out6, sizeof(double) * 6);
@@ -352,6 +354,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     CK(cudaMemset(h->progress, 0, sizeof(int) * T));
     CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
     CK(cudaMemset(h->unit_counter, 0, sizeof(int)));
+    CK(cudaMemset(h->hand, 0, sizeof(double2) * (size_t)n * T * d));
     CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits));
     {
         const char* v = getenv("TAME_SWEEP");   // "panel" forces the stream-ordered per-panel path (debug / comparison)
@@ -364,7 +367,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
-    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0;
+    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand;
 
     h->nb_ll = h->ops->llmse_blocks(P);
     h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
@@ -381,7 +384,7 @@ int tame_destroy(tame_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : {(void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
-                    (void*)h->unit_counter, (void*)h->unit_done})
+                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand})
         if (p) cudaFree(p);
     if (h->out6_pinned) cudaFreeHost(h->out6_pinned);
     if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
@@ -444,9 +447,9 @@ int tame_sweep(tame_handle* h) {
     // running totals of the partner moments from the current means; resets the progress counters
     ops->totals(P, h->tot_partial, h->NS, st);
     ev_mark(h, 1);
+    h->P.epoch = ++h->epoch;   // stamps of this sweep (hand-over tags, unit_done)
     if (h->fused) {
         // single GPU: the whole sweep is one persistent cooperative launch (chain CTAs + streaming CTAs)
-        h->P.epoch = ++h->epoch;
         ev_mark(h, 2);
         cudaError_t e = ops->sweep_fused(h->P, st);
         if (e != cudaSuccess) return fail(TAME_ECUDA, "fused sweep launch: %s", cudaGetErrorString(e));
