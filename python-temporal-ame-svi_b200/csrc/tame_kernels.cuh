@@ -298,34 +298,50 @@ __global__ void __launch_bounds__(256, 1) k_contract(TameParams P, int k0, int k
 
 // ------------------------------------------------------------------------------------------------------
 // warp-level in-place Gauss-Jordan inverse of a symmetric positive-definite DxD matrix.
-// lane c (< D) holds column c in col[0..D-1].  At step k every lane publishes its element of pivot row k,
-// the whole row is read back as a shared-memory broadcast, and column k is reconstructed from the row by the
-// (anti)symmetry of the partially swept matrix ( M[r][k] = -M[k][r] for swept r<k, +M[k][r] otherwise ).
-// Returns sum_k log(pivot_k) = logdet when WANT_LOGDET.  rowb: 2*(D+2) doubles of per-warp shared memory.
+// lane c (< D) holds column c in col[0..D-1].  At step k every lane publishes its element of pivot row k, the
+// whole row is read back as a shared-memory broadcast, and column k is reconstructed from the row by the
+// (anti)symmetry of the partially swept matrix ( M[r][k] = -M[k][r] for swept r<k, +M[k][r] otherwise; the
+// publishing lane applies the sign ).  The loop over pivots is ROLLED (one step is ~100 instructions, so the
+// chain's inner loop stays inside the instruction cache): the row registers rotate by one position per step so the
+// pivot row is always col[0] and all register indices stay compile-time; the published row is stored twice so the
+// rotated read needs no modulo.  After D steps the rows are back in place.
+// Returns sum_k log(pivot_k) = logdet when WANT_LOGDET.  rowb: 4*D doubles of per-warp shared memory.
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tame_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 template <int D, bool WANT_LOGDET>
 __device__ __forceinline__ double tame_gj_inverse(double (&col)[D], double* rowb, int lane) {
-    constexpr int RB = D + 2;
     double logdet = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < D; ++k) {
-        double* rb = rowb + (k & 1) * RB;
-        if (lane < D) rb[lane] = col[k];
+        double* rb = rowb + (k & 1) * (2 * D);
+        if (lane < D) {
+            const double v = (lane < k) ? -col[0] : col[0];
+            rb[lane] = v;
+            rb[lane + D] = v;
+        }
         __syncwarp();
-        double rk[D];
-#pragma unroll
-        for (int r = 0; r < D; ++r) rk[r] = rb[r];
-        const double piv = 1.0 / rk[k];
-        if (WANT_LOGDET) logdet += log(rk[k]);
-        const double s = col[k] * piv;
+        const double* rr = rb + k;          // rr[p]: signed pivot-row element of original index (k+p) mod D
+        const double pivv = rr[0];
+        const double piv = tame_rcp(pivv);
+        if (WANT_LOGDET) logdet += log(pivv);
+        const double s = col[0] * piv;
         const bool isk = (lane == k);
 #pragma unroll
-        for (int r = 0; r < D; ++r) {
-            if (r == k) continue;
-            const double f = (r < k) ? -rk[r] : rk[r];
-            col[r] = isk ? (-f * piv) : fma(-f, s, col[r]);
+        for (int p = 1; p < D; ++p) {
+            const double f = rr[p];
+            col[p - 1] = isk ? (-f * piv) : fma(-f, s, col[p]);
         }
-        col[k] = isk ? piv : s;
+        col[D - 1] = isk ? piv : s;
     }
     return logdet;
 }
@@ -335,10 +351,11 @@ template <int R>
 struct TameChainSmem {
     static constexpr int D = 2 + 2 * R, NV = 2 * R, MP = NV + 2, TOT = TameTot<R>::TOT, DP = D + 1;
     double ring[TAME_WIN][MP];   // z = [V,U] of the window's already updated nodes at this warp's time step
-    double tot[TOT];             // g (NV) then G (NV x NV)
-    double rowb[2 * (D + 2)];
+    double rowb[4 * D];
     double Cm[D * DP];
     double Cf[D * D];
+    double cstc[D * 32];         // constant part of the precision: cstc[k*32 + lane] = column `lane`, row k
+    double cold[2][D * D + 2];   // old covariance of the current / next node (cp.async double buffer)
     double wbuf[TAME_WIN * 2];
     double mold[D], mnew[D], mprev[D], mnext[D], hvec[D], hin[NV];
 };
@@ -346,22 +363,6 @@ struct TameChainSmem {
 // z component x of a mean vector held in shared memory
 template <int R>
 __device__ __forceinline__ double tame_zof(const double* m, int x) { return m[tame_zidx<R>(x)]; }
-
-// tot += sign * (z, z z')
-template <int R>
-__device__ __forceinline__ void tame_tot_update(double* tot, const double* m, double sign, int lane) {
-    constexpr int NV = 2 * R, TOT = TameTot<R>::TOT;
-    for (int e = lane; e < TOT; e += 32) {
-        double term;
-        if (e < NV) {
-            term = tame_zof<R>(m, e);
-        } else {
-            int f = e - NV;
-            term = tame_zof<R>(m, f / NV) * tame_zof<R>(m, f % NV);
-        }
-        tot[e] = fma(sign, term, tot[e]);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------
 // k_chain: the Gauss-Seidel chain over nodes [i0,i1) (one panel, i1-i0 <= TAME_WIN, owned by this rank).
@@ -395,7 +396,6 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     const int c = lane;   // column / component owned by this lane
 
     // constant part of the precision, column c:  (t==0 ? S0inv : Qinv) + (t<T-1 ? Phi'QinvPhi : 0)
-    double cstcol[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         double v = 0.0;
@@ -403,9 +403,27 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             v = has_prev ? P.cst[1 * D * D + k * D + c] : P.cst[0 * D * D + k * D + c];
             if (has_next) v += P.cst[2 * D * D + k * D + c];
         }
-        cstcol[k] = v;
+        sm.cstc[k * 32 + lane] = v;
     }
-    for (int e = lane; e < TOT; e += 32) sm.tot[e] = P.tot[(size_t)t * TOT + e];
+    // running partner moments of this time step, held in registers: lane c >= 2 owns column y = c-2 of
+    // G = sum_j z_j z_j' (and g[y]); lanes 0,1 hold g = sum_j z_j  (z_j = [V_j, U_j]) -- exactly what the lane needs
+    // to form its column of the observation precision.
+    double Gc[NV], gy = 0.0;
+#pragma unroll
+    for (int x = 0; x < NV; ++x) {
+        double v = 0.0;
+        if (c < 2) v = P.tot[(size_t)t * TOT + x];
+        else if (c < D) v = P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)];
+        Gc[x] = v;
+    }
+    if (c >= 2 && c < D) gy = P.tot[(size_t)t * TOT + (c - 2)];
+    // tot += sign * (z, z z') for the mean vector m (shared memory)
+    auto tot_update = [&](const double* m, double sign) {
+        const double zy = (c < 2) ? sign : ((c < D) ? sign * m[tame_zidx<R>(c - 2)] : 0.0);
+#pragma unroll
+        for (int x = 0; x < NV; ++x) Gc[x] = fma(m[tame_zidx<R>(x)], zy, Gc[x]);
+        if (c >= 2) gy += zy;
+    };
     // scale pattern of P_obs (see header): rows x<R of the z-block use sA, rows x>=R use sB
     double sA, sB;
     if (c == 0) { sA = P.p0; sB = P.q; }
@@ -424,7 +442,6 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 
     // prefetch registers for node i
     double2 yv[NWS];
-    double cold[NE];
     double mold = 0.0, mnext = 0.0;
     auto prefetch = [&](int i) {
         const int l = tame_lrow(i, P.panel, P.world);
@@ -434,11 +451,11 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             int j = wlo + lane + 32 * s;
             yv[s] = (j < i) ? tame_ld_stream2(P.Y + (((size_t)l * P.n + j) * T + t) * 2) : make_double2(0.0, 0.0);
         }
-        const double* cp = P.Xc + ((size_t)i * T + t) * D * D;
-#pragma unroll
-        for (int m = 0; m < NE; ++m) {
-            int e = lane + 32 * m;
-            cold[m] = (e < D * D) ? __ldcs(cp + e) : 0.0;
+        {   // old covariance of node i -> shared (asynchronous 16-byte copies; X_cov blocks are 16-byte aligned)
+            const double* cp = P.Xc + ((size_t)i * T + t) * D * D;
+            double* dst = sm.cold[i & 1];
+            for (int e = lane; e < (D * D) / 2; e += 32) tame_cp_async16(dst + 2 * e, cp + 2 * e, true);
+            tame_cp_async_commit();
         }
         if (c < D) {
             mold = tame_ld_cg(P.Xm + ((size_t)i * T + t) * D + c);
@@ -452,25 +469,13 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         double2 ycur[NWS];
 #pragma unroll
         for (int s = 0; s < NWS; ++s) ycur[s] = yv[s];
-        double ccur[NE];
-#pragma unroll
-        for (int m = 0; m < NE; ++m) ccur[m] = cold[m];
         const double mo = mold, mn = mnext;
         if (i + 1 < i1) prefetch(i + 1);
         // hand-over of (i, t-1): the slot carries {mean, tag}; tag ^ bits(mean) == magic proves the 16-byte slot is
         // this sweep's and untorn.  First look now (in steady state the predecessor is ahead and this hits), the
         // blocking wait comes after the inverse.
-        double mprev_c = 0.0;
-        bool have_prev = true;
-        if (has_prev) {
-            bool ok = true;
-            if (c < D) {
-                const double2 hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
-                ok = ((unsigned long long)__double_as_longlong(hv.x) ^ (unsigned long long)__double_as_longlong(hv.y)) == magic;
-                mprev_c = hv.x;
-            }
-            have_prev = __all_sync(0xffffffffu, ok);
-        }
+        double2 hv = make_double2(0.0, 0.0);
+        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
         if (FUSED && (i % TAME_SB) == 0) {
             // the static partner part H of this sub-block comes from a streaming CTA of the same launch
             if (lane == 0) {
@@ -493,31 +498,22 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 
         if (c < D) { sm.mold[c] = mo; sm.mnext[c] = mn; }
         __syncwarp();
-        tame_tot_update<R>(sm.tot, sm.mold, -1.0, lane);
-        __syncwarp();
+        tot_update(sm.mold, -1.0);
 
         // ---- precision column c
         double col[D];
         {
-            const double* g = sm.tot;
-            const double* G = sm.tot + NV;
             if (c < 2) {
                 col[0] = (c == 0) ? P.p0 * m1 : P.q * m1;
                 col[1] = (c == 0) ? P.q * m1 : P.p1 * m1;
-#pragma unroll
-                for (int x = 0; x < NV; ++x) col[2 + x] = ((x < R) ? sA : sB) * g[x];
-            } else if (c < D) {
-                const int y = c - 2;
-                col[0] = sA * g[y];
-                col[1] = sB * g[y];
-#pragma unroll
-                for (int x = 0; x < NV; ++x) col[2 + x] = ((x < R) ? sA : sB) * G[x * NV + y];
             } else {
-#pragma unroll
-                for (int k = 0; k < D; ++k) col[k] = 0.0;
+                col[0] = sA * gy;
+                col[1] = sB * gy;
             }
 #pragma unroll
-            for (int k = 0; k < D; ++k) col[k] += cstcol[k];
+            for (int x = 0; x < NV; ++x) col[2 + x] = ((x < R) ? sA : sB) * Gc[x];
+#pragma unroll
+            for (int k = 0; k < D; ++k) col[k] += sm.cstc[k * 32 + lane];
         }
         double pdiag = 0.0;
 #pragma unroll
@@ -570,22 +566,19 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             for (int k = 0; k < D; ++k) crow[k] = 0.0;
         }
 
-        // ---- wait for (i, t-1) if the early look missed
-        if (!have_prev) {
+        // ---- (i, t-1): check the early look, spin only if the predecessor is not ahead
+        if (has_prev) {
             int spins = 0;
             for (;;) {
-                bool ok = true;
-                if (c < D) {
-                    const double2 hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
-                    ok = ((unsigned long long)__double_as_longlong(hv.x) ^ (unsigned long long)__double_as_longlong(hv.y)) == magic;
-                    mprev_c = hv.x;
-                }
+                const bool ok = (c >= D) ||
+                    (((unsigned long long)__double_as_longlong(hv.x) ^ (unsigned long long)__double_as_longlong(hv.y)) == magic);
                 if (__all_sync(0xffffffffu, ok)) break;
                 if (++spins > TAME_SPIN_LIMIT) { if (lane == 0) atomicExch(P.abort_flag, 1); break; }
                 if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+                if (c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
             }
+            if (c < D) sm.mprev[c] = hv.x;
         }
-        if (has_prev && c < D) sm.mprev[c] = mprev_c;
         __syncwarp();
 
         // ---- natural parameter
@@ -629,6 +622,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         }
 
         // ---- covariance, damped write (coalesced through shared memory)
+        if (i + 1 < i1) tame_cp_async_wait<1>(); else tame_cp_async_wait<0>();   // node i's old covariance has landed
         if (c < D) {
             if (P.mode == 0) {
                 const double dinv = 1.0 / (pdiag + 1e-8);
@@ -645,15 +639,19 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 #pragma unroll
             for (int m = 0; m < NE; ++m) {
                 int e = lane + 32 * m;
-                if (e < D * D) __stcs(cp + e, lr * sm.Cf[e] + om * ccur[m]);
+                if (e < D * D) __stcs(cp + e, lr * sm.Cf[e] + om * sm.cold[i & 1][e]);
             }
         }
         // ---- totals with the new mean, window ring
-        tame_tot_update<R>(sm.tot, sm.mnew, 1.0, lane);
+        tot_update(sm.mnew, 1.0);
         if (lane < NV) sm.ring[i & (TAME_WIN - 1)][lane] = tame_zof<R>(sm.mnew, lane);
         __syncwarp();
     }
-    for (int e = lane; e < TOT; e += 32) P.tot[(size_t)t * TOT + e] = sm.tot[e];
+    if (c >= 2 && c < D) {
+        P.tot[(size_t)t * TOT + (c - 2)] = gy;
+#pragma unroll
+        for (int x = 0; x < NV; ++x) P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)] = Gc[x];
+    }
 }
 
 
@@ -890,7 +888,7 @@ template <int R>
 __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0, double logdetQ, double* partial) {
     constexpr int D = 2 + 2 * R, NE = (D * D + 31) / 32;
     __shared__ double Cm[8][D * D];
-    __shared__ double rowb[8][2 * (D + 2)];
+    __shared__ double rowb[8][4 * D];
     __shared__ double vec[8][2 * D];
     __shared__ double red[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
