@@ -341,6 +341,9 @@ def run_ours(args, shape):
         kt += np.array([x.value for x in tm])
     e1.record()
     barrier()
+    probes = (C.c_uint64 * 16)()
+    lib.tame_debug_probes(h, probes)
+    probes = list(probes)
     ms = e0.elapsed_time(e1)
     launches = lib.tame_launch_count() - launches0
     if world > 1:
@@ -405,7 +408,7 @@ def run_ours(args, shape):
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_unit": 32},
                          "kernels_ms_per_step": {"sweep_total": kt[0], "elbo_total": kt[1], "k_contract": kt[2], ("k_sweep" if fused else "k_chain"): kt[3], "k_llmse": kt[4]},
                          "k_llmse": {"achieved": llmse_gbs, "frac": (llmse_gbs / peak) if llmse_gbs else None}},
-            "clocks": clocks, "gpu_launches": int(launches), "elbo_trace_tail": elbos[-2:],
+            "clocks": clocks, "gpu_launches": int(launches), "elbo_trace_tail": elbos[-2:], "chain_probes": probes,
         }
         if e2e:
             line["e2e"] = e2e

@@ -139,6 +139,10 @@ int tame_gather_state(tame_handle* h);
 int tame_last_timing(tame_handle* h, double* sweep_ms, double* elbo_ms, double* contract_ms, double* chain_ms,
                      double* llmse_ms);
 int tame_set_timing(tame_handle* h, int32_t enabled);
+/* timing probes of the last fused sweep (k_sweep): [0..7] time-step warp 0, [8..15] warp T-1:
+ * {start ns, first-node ns, end ns, cycles waiting for streaming units, cycles waiting for the hand-over,
+ *  cycles in the block inverse, nodes, (slot 7 only) kernel start ns} */
+int tame_debug_probes(tame_handle* h, uint64_t* out16_host);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,7 @@ struct tame_handle {
     int epoch = 0;
     bool fused = true;
     double2* hand = nullptr;
+    unsigned long long* dbg = nullptr;
     int NS = 1, nb_ll = 0, nb_cell = 0;
     double* out6_pinned = nullptr;
     int* abort_pinned = nullptr;
@@ -343,6 +344,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     if (e == cudaSuccess) e = dalloc((void**)&h->abort_flag, sizeof(int));
     const size_t nunits = (size_t)((n + TAME_SB - 1) / TAME_SB) * ((T + 31) / 32);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_counter, sizeof(int));
+    if (e == cudaSuccess) e = dalloc((void**)&h->dbg, sizeof(unsigned long long) * 16);
     if (e == cudaSuccess) e = dalloc((void**)&h->hand, sizeof(double2) * (size_t)n * T * d);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits);
     if (e == cudaSuccess) e = dalloc((void**)&h->red6, sizeof(double) * 6);
@@ -354,6 +356,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     CK(cudaMemset(h->progress, 0, sizeof(int) * T));
     CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
     CK(cudaMemset(h->unit_counter, 0, sizeof(int)));
+    CK(cudaMemset(h->dbg, 0, sizeof(unsigned long long) * 16));
     CK(cudaMemset(h->hand, 0, sizeof(double2) * (size_t)n * T * d));
     CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits));
     {
@@ -367,7 +370,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
-    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand;
+    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg;
 
     h->nb_ll = h->ops->llmse_blocks(P);
     h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
@@ -384,7 +387,7 @@ int tame_destroy(tame_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : {(void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
-                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand})
+                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg})
         if (p) cudaFree(p);
     if (h->out6_pinned) cudaFreeHost(h->out6_pinned);
     if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
@@ -627,6 +630,14 @@ int tame_gather_state(tame_handle* h) {
         NK(g_nccl.Broadcast(h->P.Xc + b * blk, h->P.Xc + b * blk, blk, ncclDouble, b % h->P.world, h->comm, h->stream));
     NK(g_nccl.GroupEnd());
     CK(cudaStreamSynchronize(h->stream));
+    return TAME_OK;
+}
+
+int tame_debug_probes(tame_handle* h, uint64_t* out16_host) {
+    if (!h || !out16_host) return fail(TAME_EINVAL, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out16_host, h->dbg, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
     return TAME_OK;
 }
 

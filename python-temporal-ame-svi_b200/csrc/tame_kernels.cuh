@@ -24,8 +24,9 @@
 #include <math_constants.h>
 #include <stdint.h>
 
-#define TAME_WIN 64          // inline window of the chain kernel (nodes)
-#define TAME_CHAIN_WPC 8     // warps (time steps) per chain CTA
+#define TAME_WIN 64          // node block of the stand-alone chain launches (multi-GPU path)
+#define TAME_RING 128        // ring of new partner vectors kept per time-step warp (>= the widest inline window)
+#define TAME_CHAIN_WPC 4     // warps (time steps) per chain CTA: one per SM sub-partition, no issue/FP64 contention
 #define TAME_SPIN_LIMIT (1 << 24)
 #define TAME_SB 32           // sub-block of the fused sweep: rows per streaming unit, push granularity
 
@@ -42,6 +43,7 @@ struct TameParams {
     int* progress;            // (T) nodes finished in this sweep by the warp of time t
     int* abort_flag;
     // fused sweep (k_sweep): work distribution between the chain CTAs and the streaming CTAs
+    unsigned long long* dbg;  // 16 timing slots (ns / cycles) written by the first and last time-step warps
     double2* hand;            // (n,T,D) hand-over slots {new mean, tag}: the flag travels with the data
     int* unit_counter;        // next (sub-block, t-slice) unit to hand to a streaming CTA
     int* unit_done;           // (nsb * nslices) epoch stamp written when a unit's H rows are complete
@@ -63,6 +65,11 @@ __device__ __forceinline__ int tame_ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long tame_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ double2 tame_ld_volatile2(const double2* p) {
     double2 v;
@@ -308,40 +315,55 @@ __global__ void __launch_bounds__(256, 1) k_contract(TameParams P, int k0, int k
 // Returns sum_k log(pivot_k) = logdet when WANT_LOGDET.  rowb: 4*D doubles of per-warp shared memory.
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double tame_rcp(double x) {
+    // rcp.approx.ftz.f64 carries ~20 bits (measured 9.9e-7 on B200); one cubic (Halley) step reaches 2.2e-16
+    // (tools/ubench_fp64.cu): r' = r (1 + e + e^2), e = 1 - x r.  24 + 3*8.8 cycles instead of 76 for IEEE division.
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    const double e = fma(-x, r, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(r, e2, r);
 }
+
+#define TAME_GJ_ROWB(D) (2 * (2 * (D) + 32))   // doubles of per-warp shared memory used by tame_gj_inverse
 
 template <int D, bool WANT_LOGDET>
 __device__ __forceinline__ double tame_gj_inverse(double (&col)[D], double* rowb, int lane) {
+    constexpr int RB = 2 * D + 32;
     double logdet = 0.0;
+    // every lane publishes (lanes >= D into a scratch slot) so the loop body has no divergent region
+    const int slot0 = (lane < D) ? lane : 2 * D + (lane - D), slot1 = (lane < D) ? lane + D : 2 * D + (lane - D);
+    rowb[slot0] = col[0];
+    rowb[slot1] = col[0];
 #pragma unroll 1
     for (int k = 0; k < D; ++k) {
-        double* rb = rowb + (k & 1) * (2 * D);
-        if (lane < D) {
-            const double v = (lane < k) ? -col[0] : col[0];
-            rb[lane] = v;
-            rb[lane + D] = v;
-        }
+        const double* rr = rowb + (k & 1) * RB + k;   // rr[p]: signed pivot-row element of original index (k+p) mod D
         __syncwarp();
-        const double* rr = rb + k;          // rr[p]: signed pivot-row element of original index (k+p) mod D
         const double pivv = rr[0];
+        double rk[D];
+#pragma unroll
+        for (int p = 1; p < D; ++p) rk[p] = rr[p];
+        // in the shadow of the reciprocal: the pivot column restarts from zero (its new entries are -f_r * piv) and
+        // its own pivot-row element counts as 1 (so that s = piv there)
+        const bool isk = (lane == k);
+        const double a0 = isk ? 1.0 : col[0];
+#pragma unroll
+        for (int p = 1; p < D; ++p) col[p] = isk ? 0.0 : col[p];
+        const unsigned flip = (lane <= k) ? 0x80000000u : 0u;    // rows 0..k are swept from the next step on
         const double piv = tame_rcp(pivv);
         if (WANT_LOGDET) logdet += log(pivv);
-        const double s = col[0] * piv;
-        const bool isk = (lane == k);
-#pragma unroll
-        for (int p = 1; p < D; ++p) {
-            const double f = rr[p];
-            col[p - 1] = isk ? (-f * piv) : fma(-f, s, col[p]);
+        const double s = a0 * piv;                                // new pivot-row element of this column
+        // the next pivot row's element first, published at once: the broadcast round trip of step k+1 overlaps the
+        // rest of this step's update
+        col[0] = fma(-rk[1], s, col[1]);
+        if (k + 1 < D) {
+            double* nb = rowb + ((k + 1) & 1) * RB;
+            const double v = __hiloint2double(__double2hiint(col[0]) ^ flip, __double2loint(col[0]));
+            nb[slot0] = v;
+            nb[slot1] = v;
         }
-        col[D - 1] = isk ? piv : s;
+#pragma unroll
+        for (int p = 2; p < D; ++p) col[p - 1] = fma(-rk[p], s, col[p]);
+        col[D - 1] = s;
     }
     return logdet;
 }
@@ -350,13 +372,13 @@ __device__ __forceinline__ double tame_gj_inverse(double (&col)[D], double* rowb
 template <int R>
 struct TameChainSmem {
     static constexpr int D = 2 + 2 * R, NV = 2 * R, MP = NV + 2, TOT = TameTot<R>::TOT, DP = D + 1;
-    double ring[TAME_WIN][MP];   // z = [V,U] of the window's already updated nodes at this warp's time step
-    double rowb[4 * D];
+    double ring[TAME_RING][MP];  // z = [V,U] of the last TAME_RING updated nodes at this warp's time step
+    double rowb[TAME_GJ_ROWB(D)];
     double Cm[D * DP];
     double Cf[D * D];
     double cstc[D * 32];         // constant part of the precision: cstc[k*32 + lane] = column `lane`, row k
     double cold[2][D * D + 2];   // old covariance of the current / next node (cp.async double buffer)
-    double wbuf[TAME_WIN * 2];
+    double wbuf[TAME_RING * 2];
     double mold[D], mnew[D], mprev[D], mnext[D], hvec[D], hin[NV];
 };
 
@@ -378,16 +400,19 @@ __device__ __forceinline__ double tame_zof(const double* m, int x) { return m[ta
 template <int R, bool FUSED>
 __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned char* smem_raw, int cta, int i0, int i1) {
     using S = TameChainSmem<R>;
-    // inline window: FUSED  -> previous + current 32-node sub-block (the streaming CTAs cover everything older),
+    // inline window: FUSED  -> the two previous + the current 32-node sub-block (the streaming CTAs cover everything
+    //                          older; two sub-blocks of slack absorb the ~1 node/time-step stagger of the warps),
     //                !FUSED -> the current 64-node block only (earlier blocks were pushed by k_contract launches)
     constexpr int WSB = FUSED ? TAME_SB : TAME_WIN;
-    constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP, NE = (D * D + 31) / 32, NWS = TAME_WIN / 32;
+    constexpr int WBACK = FUSED ? 2 : 0;
+    constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP, NE = (D * D + 31) / 32, NWS = FUSED ? 3 : 2;
     double* cstQP = reinterpret_cast<double*>(smem_raw);          // QinvPhi   (D*D)
     double* cstPQ = cstQP + D * D;                                // Phi'Qinv  (D*D)
     S* warps = reinterpret_cast<S*>(cstPQ + D * D);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < 2 * D * D; e += blockDim.x) cstQP[e] = P.cst[3 * D * D + e];
     __syncthreads();
+    if (warp >= TAME_CHAIN_WPC) return;      // chain CTAs of k_sweep carry 8 warps; only one per sub-partition works
     const int t = cta * TAME_CHAIN_WPC + warp;
     if (t >= P.T) return;
     S& sm = warps[warp];
@@ -437,7 +462,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     const unsigned long long magic = 0x5AFE000000000000ull + (unsigned long long)(unsigned)P.epoch;
     const double2* hand_prev = P.hand + (size_t)(t - 1) * D + min(c, D - 1);   // + i*T*D : slot of (i, t-1), lane c
     double2* hand_mine = P.hand + (size_t)t * D + min(c, D - 1);
-    auto window_lo = [&](int i) { return FUSED ? max(0, (i / WSB - 1) * WSB) : (i / WSB) * WSB; };
+    auto window_lo = [&](int i) { return max(0, (i / WSB - WBACK) * WSB); };
     const int nslices = (T + 31) / 32;
 
     // prefetch registers for node i
@@ -463,6 +488,10 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         }
     };
     prefetch(i0);
+    const bool probe = FUSED && lane == 0 && (t == 0 || t == T - 1);     // timing probes (dbg[0..7]: t=0, [8..15]: t=T-1)
+    unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
+    long long wait_unit = 0, wait_hand = 0, t_gj = 0;
+    if (probe) dbg[0] = tame_globaltimer();
 
     for (int i = i0; i < i1; ++i) {
         // ---- take the prefetched values, start the next node's loads
@@ -471,13 +500,11 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         for (int s = 0; s < NWS; ++s) ycur[s] = yv[s];
         const double mo = mold, mn = mnext;
         if (i + 1 < i1) prefetch(i + 1);
-        // hand-over of (i, t-1): the slot carries {mean, tag}; tag ^ bits(mean) == magic proves the 16-byte slot is
-        // this sweep's and untorn.  First look now (in steady state the predecessor is ahead and this hits), the
-        // blocking wait comes after the inverse.
-        double2 hv = make_double2(0.0, 0.0);
-        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
+        // (hand-over of (i, t-1): the slot carries {mean, tag}; tag ^ bits(mean) == magic proves the 16-byte slot is this
+        //  sweep's and untorn -- see "first look" below.)
         if (FUSED && (i % TAME_SB) == 0) {
             // the static partner part H of this sub-block comes from a streaming CTA of the same launch
+            const long long c0 = clock64();
             if (lane == 0) {
                 const int* flag = P.unit_done + (i / TAME_SB) * nslices + (t >> 5);
                 int spins = 0;
@@ -487,6 +514,8 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
                 }
             }
             __syncwarp();
+            wait_unit += clock64() - c0;
+            if (probe && i == 0) dbg[1] = tame_globaltimer();
         }
         double hb = 0.0;
         {
@@ -534,14 +563,20 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             if (x < NV) {
                 const int wsel = (x < R) ? 0 : 1;
                 for (int jj = half; jj < cnt; jj += 2)
-                    acc = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_WIN - 1)][x], acc);
+                    acc = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][x], acc);
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             if (lane < NV) sm.hin[lane] = acc;
         }
 
+        // ---- first look at the hand-over slot of (i, t-1); it is checked after the inverse
+        double2 hv = make_double2(0.0, 0.0);
+        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
+
         // ---- inverse
+        const long long cg0 = clock64();
         tame_gj_inverse<D, false>(col, sm.rowb, lane);
+        t_gj += clock64() - cg0;
 
         // ---- factorisation rule -> row c of the new covariance in crow[]
         double crow[D];
@@ -569,6 +604,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         // ---- (i, t-1): check the early look, spin only if the predecessor is not ahead
         if (has_prev) {
             int spins = 0;
+            const long long c0 = clock64();
             for (;;) {
                 const bool ok = (c >= D) ||
                     (((unsigned long long)__double_as_longlong(hv.x) ^ (unsigned long long)__double_as_longlong(hv.y)) == magic);
@@ -578,6 +614,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
                 if (c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
             }
             if (c < D) sm.mprev[c] = hv.x;
+            wait_hand += clock64() - c0;
         }
         __syncwarp();
 
@@ -644,8 +681,15 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         }
         // ---- totals with the new mean, window ring
         tot_update(sm.mnew, 1.0);
-        if (lane < NV) sm.ring[i & (TAME_WIN - 1)][lane] = tame_zof<R>(sm.mnew, lane);
+        if (lane < NV) sm.ring[i & (TAME_RING - 1)][lane] = tame_zof<R>(sm.mnew, lane);
         __syncwarp();
+    }
+    if (probe) {
+        dbg[2] = tame_globaltimer();
+        dbg[3] = (unsigned long long)wait_unit;
+        dbg[4] = (unsigned long long)wait_hand;
+        dbg[5] = (unsigned long long)t_gj;
+        dbg[6] = (unsigned long long)(i1 - i0);
     }
     if (c >= 2 && c < D) {
         P.tot[(size_t)t * TOT + (c - 2)] = gy;
@@ -668,9 +712,9 @@ __global__ void __launch_bounds__(TAME_CHAIN_WPC * 32, 1) k_chain(TameParams P, 
 //   the remaining CTAs       are streaming workers.  A unit = (32-row sub-block sb, 32-step time slice).  A worker
 //       takes units in ascending order from an atomic counter, keeps the unit's 32 x 32 x 2R partner sums in
 //       registers, streams  (a) the static upper part j > k (partners still carrying their old means when row k
-//       is updated) immediately and (b) the lower columns j < (sb-1)*32 (new means) as the chain's progress
+//       is updated) immediately and (b) the lower columns j < (sb-2)*32 (new means) as the chain's progress
 //       counters release them, then writes H once (no read-modify-write, no atomics) and stamps unit_done.
-//   The chain waits for a sub-block's stamp before entering it and covers the last (up to) 64 partners inline.
+//   The chain waits for a sub-block's stamp before entering it and covers the last (up to) 96 partners inline.
 // Every Y entry is read exactly once per sweep; the schedule is the reference's.
 // grid = n_chain_ctas + workers (all co-resident), block 256, dynamic smem = max of the two roles.
 // ------------------------------------------------------------------------------------------------------
@@ -678,6 +722,7 @@ template <int R, int RW>
 __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(8 * RW == TAME_SB, "a streaming unit is one sub-block of rows");
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.dbg[7] = tame_globaltimer();
     if ((int)blockIdx.x < P.n_chain_ctas) {
         tame_chain_body<R, true>(P, smem_raw, blockIdx.x, 0, P.n);
         return;
@@ -712,7 +757,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
         // (a) static upper part
         tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, ((kbase + 1) / JC) * JC, P.n, true, accA, accB);
         // (b) lower columns, released by the chain
-        const int lowend = max(0, (sb - 1) * TAME_SB);
+        const int lowend = max(0, (sb - 2) * TAME_SB);
         int done_cols = 0, spins = 0;
         bool dead = false;
         while (done_cols < lowend && !dead) {
@@ -888,7 +933,7 @@ template <int R>
 __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0, double logdetQ, double* partial) {
     constexpr int D = 2 + 2 * R, NE = (D * D + 31) / 32;
     __shared__ double Cm[8][D * D];
-    __shared__ double rowb[8][4 * D];
+    __shared__ double rowb[8][TAME_GJ_ROWB(D)];
     __shared__ double vec[8][2 * D];
     __shared__ double red[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
