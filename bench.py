@@ -249,18 +249,11 @@ def init_state(n, T, d, dev, seed=42):
     return Xm, Xc
 
 
-def owned_rows(n, panel, world, rank):
-    rows = []
-    for b in range((n + panel - 1) // panel):
-        if b % world == rank:
-            rows.append((b * panel, min(n, (b + 1) * panel)))
-    return rows
-
-
 def run_ours(args, shape):
     import torch
     import torch.distributed as dist
     from tame_b200 import _lib
+    from tame_b200.sharding import owned_rows
     lib = _lib.load()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -91,16 +91,16 @@ def derived_constants(c):
 # ----------------------------------------------------------------------------------
 # sweep (literal schedule)
 # ----------------------------------------------------------------------------------
-def observation_terms(Y, Xm, i, t, R_inv, r):
+def observation_terms(Y, Xm, i, t, R_inv, r, row=None):
     """structured_mf.py:289-326.  P_obs = sum_{j!=i} J_j' R^-1 J_j, h_obs = sum J_j' R^-1 y_ij with
     J_j = [[1,0,V_j,0],[0,1,0,U_j]] built from the partners' CURRENT means at time t."""
-    n = Y.shape[0]
+    n = Y.shape[1]
     d = 2 + 2 * r
     mask = np.ones(n, dtype=bool)
     mask[i] = False
     U = Xm[mask, t, 2:2 + r]
     V = Xm[mask, t, 2 + r:]
-    y = Y[i, mask, t, :]                       # (n-1, 2)
+    y = Y[i if row is None else row, mask, t, :]   # (n-1, 2); `row`: storage row of node i in a sharded Y
     m = n - 1
     J = np.zeros((m, 2, d))
     J[:, 0, 0] = 1.0
@@ -113,12 +113,12 @@ def observation_terms(Y, Xm, i, t, R_inv, r):
     return P, h
 
 
-def update_node(Y, Xm, Xc, i, c, lr, mode):
+def update_node(Y, Xm, Xc, i, c, lr, mode, row=None):
     """structured_mf.py:220-287 (good/bad) and naive_mf.py:207-282 (naive), in place."""
     T, r, d = c["T"], c["r"], c["d"]
     Phi, Q_inv, S0_inv, R_inv = c["Phi"], c["Q_inv"], c["S0_inv"], c["R_inv"]
     for t in range(T):
-        P, h = observation_terms(Y, Xm, i, t, R_inv, r)
+        P, h = observation_terms(Y, Xm, i, t, R_inv, r, row)
         if t == 0:
             P = P + S0_inv
         if t > 0:
@@ -146,6 +146,23 @@ def sweep(Y, Xm, Xc, c, lr, mode):
     """structured_mf.py:211-218: Gauss-Seidel over nodes 0..n-1, times 0..T-1 inside."""
     for i in range(c["n"]):
         update_node(Y, Xm, Xc, i, c, lr, mode)
+
+
+def sweep_sharded(Y_local, Xm, Xc, c, lr, mode, world, rank, panel, broadcast):
+    """The multi-GPU schedule on one rank: nodes in order; the owner of a panel updates its nodes from ITS rows of Y
+    (Y_local in storage order) and the replicated means, then `broadcast(root, array)` ships the panel's new means.
+    X_cov rows of foreign nodes are left untouched (tame_gather_state collects them).  Same schedule as `sweep`."""
+    n = c["n"]
+    for lo in range(0, n, panel):
+        hi = min(n, lo + panel)
+        owner = (lo // panel) % world
+        if owner == rank:
+            for i in range(lo, hi):
+                b = i // panel
+                update_node(Y_local, Xm, Xc, i, c, lr, mode, row=(b // world) * panel + (i - b * panel))
+        blk = np.ascontiguousarray(Xm[lo:hi])
+        broadcast(owner, blk)
+        Xm[lo:hi] = blk
 
 
 # ----------------------------------------------------------------------------------

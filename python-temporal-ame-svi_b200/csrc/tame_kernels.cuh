@@ -545,8 +545,10 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             for (int k = 0; k < D; ++k) col[k] += sm.cstc[k * 32 + lane];
         }
         double pdiag = 0.0;
+        if (P.mode == 0) {          // naive rule needs diag(P) (naive_mf.py:271-274)
 #pragma unroll
-        for (int k = 0; k < D; ++k) pdiag = (k == c) ? col[k] : pdiag;
+            for (int k = 0; k < D; ++k) pdiag = (k == c) ? col[k] : pdiag;
+        }
 
         // ---- inline window: partners of this panel that were already updated (new means, same time step)
         {
@@ -560,10 +562,19 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             const int cnt = i - wlo;
             const int x = lane & 15, half = lane >> 4;
             double acc = 0.0;
-            if (x < NV) {
-                const int wsel = (x < R) ? 0 : 1;
-                for (int jj = half; jj < cnt; jj += 2)
-                    acc = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][x], acc);
+            {
+                // lane = (component x, parity of the window slot); four independent partial sums per lane
+                const int xx = min(x, NV - 1), wsel = (xx < R) ? 0 : 1;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int jj = half;
+                for (; jj + 6 < cnt; jj += 8) {
+                    a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
+                    a1 = fma(sm.wbuf[(jj + 2) * 2 + wsel], sm.ring[(wlo + jj + 2) & (TAME_RING - 1)][xx], a1);
+                    a2 = fma(sm.wbuf[(jj + 4) * 2 + wsel], sm.ring[(wlo + jj + 4) & (TAME_RING - 1)][xx], a2);
+                    a3 = fma(sm.wbuf[(jj + 6) * 2 + wsel], sm.ring[(wlo + jj + 6) & (TAME_RING - 1)][xx], a3);
+                }
+                for (; jj < cnt; jj += 2) a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
+                acc = (x < NV) ? (a0 + a1) + (a2 + a3) : 0.0;
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             if (lane < NV) sm.hin[lane] = acc;
@@ -620,29 +631,50 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 
         // ---- natural parameter
         double hval = 0.0;
-        if (c < D) {
-            hval = hb + ((c >= 2) ? sm.hin[c - 2] : 0.0);
+        {
+            // all lanes run the two AR mat-vecs (lanes >= D on row D-1, result discarded): no divergent region, and
+            // three partial sums each so the dependent FMA chains are D/3 long
+            const int cc = min(c, D - 1);
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0;
             if (has_prev) {
-                double a = 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) a = fma(cstQP[c * D + k], sm.mprev[k], a);
-                hval += a;
+                for (int k = 0; k + 2 < D; k += 3) {
+                    p0 = fma(cstQP[cc * D + k], sm.mprev[k], p0);
+                    p1 = fma(cstQP[cc * D + k + 1], sm.mprev[k + 1], p1);
+                    p2 = fma(cstQP[cc * D + k + 2], sm.mprev[k + 2], p2);
+                }
+#pragma unroll
+                for (int k = (D / 3) * 3; k < D; ++k) p0 = fma(cstQP[cc * D + k], sm.mprev[k], p0);
             }
             if (has_next) {
-                double a = 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) a = fma(cstPQ[c * D + k], sm.mnext[k], a);
-                hval += a;
+                for (int k = 0; k + 2 < D; k += 3) {
+                    n0 = fma(cstPQ[cc * D + k], sm.mnext[k], n0);
+                    n1 = fma(cstPQ[cc * D + k + 1], sm.mnext[k + 1], n1);
+                    n2 = fma(cstPQ[cc * D + k + 2], sm.mnext[k + 2], n2);
+                }
+#pragma unroll
+                for (int k = (D / 3) * 3; k < D; ++k) n0 = fma(cstPQ[cc * D + k], sm.mnext[k], n0);
             }
-            sm.hvec[c] = hval;
+            hval = hb + ((c >= 2 && c < D) ? sm.hin[c - 2] : 0.0);
+            hval += (p0 + p1) + p2;          // Qinv Phi mu_{t-1}      (structured_mf.py:258)
+            hval += (n0 + n1) + n2;          // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
+            if (c < D) sm.hvec[c] = hval;
         }
         __syncwarp();
 
         // ---- mean, damped write, hand-over
         if (c < D) {
-            double mu = 0.0;
+            double m0 = 0.0, m1 = 0.0, m2 = 0.0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) mu = fma(crow[k], sm.hvec[k], mu);
+            for (int k = 0; k + 2 < D; k += 3) {
+                m0 = fma(crow[k], sm.hvec[k], m0);
+                m1 = fma(crow[k + 1], sm.hvec[k + 1], m1);
+                m2 = fma(crow[k + 2], sm.hvec[k + 2], m2);
+            }
+#pragma unroll
+            for (int k = (D / 3) * 3; k < D; ++k) m0 = fma(crow[k], sm.hvec[k], m0);
+            const double mu = (m0 + m1) + m2;
             const double mnew = lr * mu + om * mo;
             tame_st_cg(P.Xm + ((size_t)i * T + t) * D + c, mnew);
             if (has_next) {
@@ -839,7 +871,13 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
         yrow[rr] = P.Y + ((size_t)l * P.n * P.T + (tv ? t : 0)) * 2;
     }
     const size_t jstride = (size_t)P.T * 2;
-    double sq = 0.0, quad = 0.0;
+    // per-row moment accumulators: upper partners (j > i) feed S00 = sum e0^2, S01 = sum e0 e1, S11 = sum e1^2 (the
+    // quadratic form is p0 S00 + 2q S01 + p1 S11), lower partners only the squared error SL.  Invalid rows / time steps
+    // are dropped in the epilogue, so the inner loop carries no per-element predicate outside the diagonal chunks.
+    double S00[RW], S01[RW], S11[RW], SL[RW];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) S00[rr] = S01[rr] = S11[rr] = SL[rr] = 0.0;
+    const int gfirst = tame_grow(min(blockIdx.y * RT, P.nloc - 1), P.panel, P.world, P.rank);   // first node of the tile
 
     auto issue_y = [&](int j, int slot) {
 #pragma unroll
@@ -866,6 +904,8 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
     }
     for (int c = 0; c < nchunks; ++c) {
         const int jc = c * JC, buf = c & 1;
+        // chunk-uniform case: 0 all partners below the tile's rows, 1 all above, 2 touches the tile's own nodes / the tail
+        const int kind = (jc + JC <= gfirst) ? 0 : ((jc > gfirst + RT - 1 && jc + JC <= P.n) ? 1 : 2);
 #pragma unroll
         for (int jj = 0; jj < JC; ++jj) {
             const int j = jc + jj;
@@ -878,7 +918,7 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
             const double aj = rec[0], bj = rec[1];
             double d0[RW], d1[RW];
 #pragma unroll
-            for (int rr = 0; rr < RW; ++rr) { d0[rr] = 0.0; d1[rr] = 0.0; }
+            for (int rr = 0; rr < RW; ++rr) { d0[rr] = oa[rr] + bj; d1[rr] = aj + ob[rr]; }   // (a_i + b_j), (a_j + b_i)
 #pragma unroll
             for (int a = 0; a < R; ++a) {
                 const double uj = rec[2 + a], vj = rec[2 + R + a];
@@ -891,12 +931,23 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
 #pragma unroll
             for (int rr = 0; rr < RW; ++rr) {
                 const double2 y = Yr[jj][rr][tid];
-                const bool ok = rv[rr] && (j < P.n) && (j != gi[rr]);
-                if (ok) {
-                    const double e0 = y.x - ((oa[rr] + bj) + d0[rr]);
-                    const double e1 = y.y - ((aj + ob[rr]) + d1[rr]);
-                    sq += e0 * e0 + e1 * e1;
-                    if (j > gi[rr]) quad += P.p0 * e0 * e0 + 2.0 * P.q * e0 * e1 + P.p1 * e1 * e1;
+                const double e0 = y.x - d0[rr], e1 = y.y - d1[rr];
+                if (kind == 1) {
+                    S00[rr] = fma(e0, e0, S00[rr]);
+                    S01[rr] = fma(e0, e1, S01[rr]);
+                    S11[rr] = fma(e1, e1, S11[rr]);
+                } else if (kind == 0) {
+                    SL[rr] = fma(e0, e0, SL[rr]);
+                    SL[rr] = fma(e1, e1, SL[rr]);
+                } else if (j < P.n && j != gi[rr]) {
+                    if (j > gi[rr]) {
+                        S00[rr] = fma(e0, e0, S00[rr]);
+                        S01[rr] = fma(e0, e1, S01[rr]);
+                        S11[rr] = fma(e1, e1, S11[rr]);
+                    } else {
+                        SL[rr] = fma(e0, e0, SL[rr]);
+                        SL[rr] = fma(e1, e1, SL[rr]);
+                    }
                 }
             }
             issue_y(j + PD, jj);
@@ -904,6 +955,14 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
         }
     }
     tame_cp_async_wait<0>();
+    double sq = 0.0, quad = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+        if (rv[rr]) {
+            sq += (S00[rr] + S11[rr]) + SL[rr];
+            quad += P.p0 * S00[rr] + 2.0 * P.q * S01[rr] + P.p1 * S11[rr];
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
