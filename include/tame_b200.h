@@ -115,6 +115,15 @@ int tame_fit_host(const tame_config* cfg, const double* Y_host, double* X_mean_h
                   int32_t max_iter, double tolerance, double* elbo_trace_host, double* mse_trace_host,
                   int32_t* n_done);
 
+/* BASELINE config 5 (experiments/sensitivity_analysis.py:117-183: many independent small fits, one per grid point
+ * and method): n_fits independent problems, each with its own tame_config and device buffers (Y_dev[f] is (n,n,T,2),
+ * X_mean_dev[f] (n,T,d), X_cov_dev[f] (n,T,d,d), updated in place).  Traces are host arrays of n_fits * max_iter
+ * doubles (row f = fit f); n_done[f] = iterations performed by fit f (early stop per fit, base.py:183-203).
+ * Fits are independent Gauss-Seidel chains, so they run concurrently on `n_streams` CUDA streams (0 = default 8). */
+int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* X_mean_dev,
+                   double* const* X_cov_dev, int32_t max_iter, double tolerance, double* elbo_traces_host,
+                   double* mse_traces_host, int32_t* n_done, int32_t n_streams);
+
 /* ---- data generation (the step before the path: TemporalAMEModel.generate_data, temporal_ame.py:200-216) - */
 /* Y[i,j,t,:] = (mu0[i,j] + e0, mu0[j,i] + e1), (e0,e1) ~ N(0, R) per unordered dyad and time, mirrored for
  * j < i, zero diagonal; mu0[i,j] = a_i + b_j + U_i.V_j from X_true (n,T,d) on the device.  Counter-based

@@ -582,6 +582,75 @@ int tame_fit_host(const tame_config* cfg, const double* Y_host, double* Xm_host,
     return rc;
 }
 
+int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* Xm_dev,
+                   double* const* Xc_dev, int32_t max_iter, double tolerance, double* elbo_traces, double* mse_traces,
+                   int32_t* n_done, int32_t n_streams) {
+    if (n_fits < 0 || (n_fits > 0 && (!cfgs || !Y_dev || !Xm_dev || !Xc_dev || !n_done))) return fail(TAME_EINVAL, "null argument");
+    if (n_streams <= 0) n_streams = 8;
+    n_streams = std::min(n_streams, std::max(n_fits, 1));
+    // one worker slot per stream: each slot drives one fit at a time, iteration by iteration; slots are advanced
+    // round-robin so the (small) kernels of different fits overlap on the device
+    struct Slot { tame_handle* h = nullptr; int fit = -1, it = 0, patience = 0; double prev = -INFINITY; cudaStream_t st = nullptr; };
+    std::vector<Slot> slots(n_streams);
+    for (auto& s : slots) CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    int next = 0, active = 0, rc = TAME_OK;
+    auto start = [&](Slot& s) -> int {
+        while (next < n_fits) {
+            const int f = next++;
+            n_done[f] = 0;
+            if (max_iter <= 0) continue;
+            int r = tame_create(&cfgs[f], &s.h);
+            if (r != TAME_OK) return r;
+            tame_set_stream(s.h, s.st);
+            r = tame_bind_Y(s.h, Y_dev[f]);
+            if (r == TAME_OK) r = tame_bind_state(s.h, Xm_dev[f], Xc_dev[f]);
+            if (r != TAME_OK) return r;
+            s.fit = f; s.it = 0; s.patience = 0; s.prev = -INFINITY;
+            ++active;
+            return TAME_OK;
+        }
+        s.fit = -1;
+        return TAME_OK;
+    };
+    for (auto& s : slots) { rc = start(s); if (rc != TAME_OK) break; }
+    while (rc == TAME_OK && active > 0) {
+        // enqueue one sweep on every active slot, then collect the ELBO/MSE of each (tame_elbo_mse synchronises its stream)
+        for (auto& s : slots) if (s.fit >= 0) { rc = tame_sweep(s.h); if (rc != TAME_OK) break; }
+        if (rc != TAME_OK) break;
+        for (auto& s : slots) {
+            if (s.fit < 0) continue;
+            double o[6];
+            rc = tame_elbo_mse(s.h, o);
+            if (rc != TAME_OK) break;
+            const int f = s.fit;
+            if (elbo_traces) elbo_traces[(size_t)f * max_iter + s.it] = o[0];
+            if (mse_traces) mse_traces[(size_t)f * max_iter + s.it] = o[5];
+            bool converged = false;
+            if (s.it > 0) {
+                const double rel = std::fabs(o[0] - s.prev) / (std::fabs(s.prev) + 1e-8);
+                s.patience = (rel < tolerance) ? s.patience + 1 : 0;
+                converged = s.patience >= 3;
+            }
+            s.prev = o[0];
+            n_done[f] = ++s.it;
+            if (converged || s.it >= max_iter) {
+                tame_destroy(s.h);
+                s.h = nullptr;
+                --active;
+                rc = start(s);
+                if (rc != TAME_OK) break;
+            }
+        }
+    }
+    std::string keep = g_err;
+    for (auto& s : slots) {
+        if (s.h) tame_destroy(s.h);
+        cudaStreamDestroy(s.st);
+    }
+    g_err = keep;
+    return rc;
+}
+
 int tame_generate_Y(int32_t n, int32_t T, int32_t r, const double R[4], const double* X_dev, uint64_t seed,
                     int32_t row_begin, int32_t row_end, double* Y_dev, void* stream) {
     if (!R || !X_dev || !Y_dev || row_begin < 0 || row_end > n || row_end < row_begin) return fail(TAME_EINVAL, "bad argument");

@@ -29,6 +29,7 @@
 #define TAME_CHAIN_WPC 4     // warps (time steps) per chain CTA: one per SM sub-partition, no issue/FP64 contention
 #define TAME_SPIN_LIMIT (1 << 24)
 #define TAME_SB 32           // sub-block of the fused sweep: rows per streaming unit, push granularity
+#define TAME_REFRESH 32      // the chain re-inverts the precision from scratch every TAME_REFRESH nodes (rank-2 updates between)
 
 struct TameParams {
     int n, T, nloc, world, rank, panel, mode;
@@ -449,6 +450,39 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         for (int x = 0; x < NV; ++x) Gc[x] = fma(m[tame_zidx<R>(x)], zy, Gc[x]);
         if (c >= 2) gy += zy;
     };
+    // raw inverse of the current precision, column c, carried from node to node
+    double cw[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) cw[k] = 0.0;
+    bool have_cw = false;
+    const double rdetR = 1.0 / (P.p0 * P.p1 - P.q * P.q);
+    const double R00 = P.p1 * rdetR, R11 = P.p0 * rdetR, R01 = -P.q * rdetR;      // R = (R^-1)^-1
+    // cw <- (P + sigma * J_z' R^-1 J_z)^-1 = cw - F (sigma R + J_z cw J_z')^-1 F',  F = cw J_z'  (z from the mean vector m)
+    auto rank2 = [&](const double* m, double sigma) {
+        double* Fs = sm.rowb;                                   // (D+14) x 2 scratch: F of every column
+        double f0 = cw[0], f1 = cw[1];
+#pragma unroll
+        for (int x = 0; x < R; ++x) f0 = fma(cw[2 + x], m[tame_zidx<R>(x)], f0);          // row c of C times g0 = (1,0,V,0)
+#pragma unroll
+        for (int x = R; x < NV; ++x) f1 = fma(cw[2 + x], m[tame_zidx<R>(x)], f1);         // row c of C times g1 = (0,1,0,U)
+        Fs[2 * lane] = f0;
+        Fs[2 * lane + 1] = f1;
+        __syncwarp();
+        double K00 = fma(sigma, R00, Fs[0]), K01 = fma(sigma, R01, Fs[1]), K11 = fma(sigma, R11, Fs[3]);
+#pragma unroll
+        for (int x = 0; x < R; ++x) {
+            const double zx = m[tame_zidx<R>(x)];
+            K00 = fma(zx, Fs[2 * (2 + x)], K00);
+            K01 = fma(zx, Fs[2 * (2 + x) + 1], K01);
+        }
+#pragma unroll
+        for (int x = R; x < NV; ++x) K11 = fma(m[tame_zidx<R>(x)], Fs[2 * (2 + x) + 1], K11);
+        const double rd = tame_rcp(K00 * K11 - K01 * K01);
+        const double v0 = (K11 * f0 - K01 * f1) * rd, v1 = (K00 * f1 - K01 * f0) * rd;
+#pragma unroll
+        for (int k = 0; k < D; ++k) cw[k] = fma(-Fs[2 * k], v0, fma(-Fs[2 * k + 1], v1, cw[k]));
+        __syncwarp();
+    };
     // scale pattern of P_obs (see header): rows x<R of the z-block use sA, rows x>=R use sB
     double sA, sB;
     if (c == 0) { sA = P.p0; sB = P.q; }
@@ -529,9 +563,11 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         __syncwarp();
         tot_update(sm.mold, -1.0);
 
-        // ---- precision column c
+        // ---- precision column c  (needed at refresh nodes; in naive mode always, for diag(P))
+        const bool refresh = !have_cw || ((i % TAME_REFRESH) == 0);
         double col[D];
-        {
+        double pdiag = 0.0;
+        if (refresh || P.mode == 0) {
             if (c < 2) {
                 col[0] = (c == 0) ? P.p0 * m1 : P.q * m1;
                 col[1] = (c == 0) ? P.q * m1 : P.p1 * m1;
@@ -543,11 +579,10 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             for (int x = 0; x < NV; ++x) col[2 + x] = ((x < R) ? sA : sB) * Gc[x];
 #pragma unroll
             for (int k = 0; k < D; ++k) col[k] += sm.cstc[k * 32 + lane];
-        }
-        double pdiag = 0.0;
-        if (P.mode == 0) {          // naive rule needs diag(P) (naive_mf.py:271-274)
+            if (P.mode == 0) {          // naive rule needs diag(P) (naive_mf.py:271-274)
 #pragma unroll
-            for (int k = 0; k < D; ++k) pdiag = (k == c) ? col[k] : pdiag;
+                for (int k = 0; k < D; ++k) pdiag = (k == c) ? col[k] : pdiag;
+            }
         }
 
         // ---- inline window: partners of this panel that were already updated (new means, same time step)
@@ -584,9 +619,21 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         double2 hv = make_double2(0.0, 0.0);
         if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
 
-        // ---- inverse
+        // ---- inverse of the precision.  P_i = P_{i-1} + G(z_{i-1}^new) - G(z_i^old) with G(z) = J_z' R^-1 J_z of rank 2, so
+        // between refreshes the carried raw inverse cw[] follows by two rank-2 (Woodbury) corrections, each with a 2x2
+        // capacitance matrix and one reciprocal; every TAME_REFRESH nodes it is recomputed from scratch (no drift).
         const long long cg0 = clock64();
-        tame_gj_inverse<D, false>(col, sm.rowb, lane);
+        if (refresh) {
+            tame_gj_inverse<D, false>(col, sm.rowb, lane);
+#pragma unroll
+            for (int k = 0; k < D; ++k) cw[k] = col[k];
+            have_cw = true;
+        } else {
+            rank2(sm.mnew, 1.0);       // node i-1 re-enters with its new mean (sm.mnew still holds it)
+            rank2(sm.mold, -1.0);      // node i leaves with its old mean
+#pragma unroll
+            for (int k = 0; k < D; ++k) col[k] = cw[k];
+        }
         t_gj += clock64() - cg0;
 
         // ---- factorisation rule -> row c of the new covariance in crow[]

@@ -232,3 +232,41 @@ def test_device_generator_distribution_and_mirror():
     assert np.allclose(cov, m.R.numpy(), atol=0.004), cov
     part = m.generate_data_device(seed=5, row_begin=32, row_end=64).cpu().numpy()
     assert np.array_equal(part, Y[32:64])
+
+
+def test_fit_batch_matches_per_fit_oracle():
+    """BASELINE config 5 in miniature: a grid of independent small fits (n, T, ar, rho vary; naive and good) through
+    tame_fit_batch, each compared with the oracle's fit() including the per-fit early stop."""
+    import ctypes as C
+    from gpu_util import make_config
+    from tame_b200 import _lib
+    lib = _lib.load()
+    grid = [(10, 5, 0.8, 0.5), (24, 8, 0.5, 0.0), (40, 3, 0.9, 0.8), (33, 12, 0.3, -0.3), (70, 4, 0.8, 0.5), (12, 20, 0.7, 0.2)]
+    fits, keep = [], []
+    for k, (n, T, ar, rho) in enumerate(grid):
+        for meth in ("naive", "good"):
+            c, Y, Xm, Xc = _random_problem(n, T, 2, seed=300 + k, rho=rho, ar=ar)
+            fits.append((c, Y, Xm, Xc, meth))
+    nf, max_iter, tol, lr = len(fits), 12, 2e-2, 0.3
+    cfgs = (_lib.TameConfig * nf)()
+    Yp, Mp, Cp = (C.c_void_p * nf)(), (C.c_void_p * nf)(), (C.c_void_p * nf)()
+    dev = []
+    for f, (c, Y, Xm, Xc, meth) in enumerate(fits):
+        cfg, kk = make_config(c, lr, orc.MODE_OF[meth])
+        keep.append(kk)
+        cfgs[f] = cfg
+        t = [torch.as_tensor(a, dtype=torch.float64).cuda().contiguous() for a in (Y, Xm, Xc)]
+        dev.append(t)
+        Yp[f], Mp[f], Cp[f] = t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr()
+    torch.cuda.synchronize()
+    el = np.zeros((nf, max_iter)); ms = np.zeros((nf, max_iter)); nd = (C.c_int32 * nf)()
+    _lib.check(lib.tame_fit_batch(nf, cfgs, Yp, Mp, Cp, max_iter, tol, _lib.dptr(el), _lib.dptr(ms), nd, 4))
+    stopped_early = 0
+    for f, (c, Y, Xm, Xc, meth) in enumerate(fits):
+        Om, Oc = Xm.copy(), Xc.copy()
+        oel, oms = orc.fit(Y, Om, Oc, c, lr, orc.MODE_OF[meth], max_iter, tol)
+        assert nd[f] == len(oel), (f, nd[f], len(oel))
+        stopped_early += len(oel) < max_iter
+        assert _trace_ok(el[f, :nd[f]], oel) and _trace_ok(ms[f, :nd[f]], oms)
+        assert rel_err(dev[f][1].cpu().numpy(), Om) < TOL and rel_err(dev[f][2].cpu().numpy(), Oc) < TOL
+    assert stopped_early > 0, "the test should exercise the per-fit early stop"
