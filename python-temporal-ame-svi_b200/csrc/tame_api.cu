@@ -97,12 +97,13 @@ struct tame_handle {
     int d = 0, nloc = 0, panel = 0;
     TameParams P{};
     cudaStream_t stream = nullptr;
-    bool y_bound = false, state_bound = false;
+    bool y_bound = false, state_bound = false, y_symmetric = false;
+    int* sym_flag = nullptr;
     // device scratch
     double *H = nullptr, *hab = nullptr, *tot = nullptr, *tot_partial = nullptr, *cst = nullptr;
     double *part_ll = nullptr, *part_cell = nullptr, *red6 = nullptr, *out6 = nullptr;
     int *progress = nullptr, *abort_flag = nullptr, *unit_counter = nullptr, *unit_done = nullptr;
-    int epoch = 0;
+    int epoch = 0, nparts = 1;
     bool fused = true;
     double2* hand = nullptr;
     unsigned long long* dbg = nullptr;
@@ -199,6 +200,22 @@ __global__ void __launch_bounds__(256) k_hab(TameParams P) {
         P.hab[((size_t)lrow * P.T + t) * 2 + 0] = r0;
         P.hab[((size_t)lrow * P.T + t) * 2 + 1] = r1;
     }
+}
+
+// Mirror check at bind time: Y[j,i,t,:] == swap(Y[i,j,t,:]) bit for bit for every i<j (the reference's generate_data
+// writes both entries from one sample, temporal_ame.py:209-216; experiments may overwrite model.Y by hand).  Single GPU
+// only (a rank holds only its own rows).  grid (ceil(T/32), n), block (32, 8); *flag is set to 1 on the first mismatch.
+__global__ void __launch_bounds__(256) k_symcheck(TameParams P, int* flag) {
+    const int i = blockIdx.y;
+    const int t = blockIdx.x * 32 + threadIdx.x;
+    if (t >= P.T) return;
+    bool bad = false;
+    for (int j = i + 1 + threadIdx.y; j < P.n; j += 8) {
+        const double2 a = tame_ld_stream2(P.Y + (((size_t)i * P.n + j) * P.T + t) * 2);
+        const double2 b = tame_ld_stream2(P.Y + (((size_t)j * P.n + i) * P.T + t) * 2);
+        bad |= (__double_as_longlong(a.x) != __double_as_longlong(b.y)) || (__double_as_longlong(a.y) != __double_as_longlong(b.x));
+    }
+    if (bad) *flag = 1;
 }
 
 // red6 = {sq, quad, lp0, lpt, ent, tr}: deterministic two-level sum of the per-block partials
@@ -336,17 +353,21 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     auto dalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 16)); };
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = dalloc((void**)&h->cst, sizeof(double) * c.size());
-    if (e == cudaSuccess) e = dalloc((void**)&h->H, sizeof(double) * (size_t)nloc * T * 2 * cfg->r);
+    // column parts per streaming unit: split the (long) upper part so that the first sub-blocks are ready early
+    h->nparts = (world == 1 && n >= 2048) ? 4 : 1;
+    if (const char* v = getenv("TAME_NPARTS")) h->nparts = std::max(1, std::min(TAME_MAX_PARTS, atoi(v)));
+    if (e == cudaSuccess) e = dalloc((void**)&h->H, sizeof(double) * (size_t)nloc * T * 2 * cfg->r * h->nparts);
     if (e == cudaSuccess) e = dalloc((void**)&h->hab, sizeof(double) * (size_t)nloc * T * 2);
     if (e == cudaSuccess) e = dalloc((void**)&h->tot, sizeof(double) * (size_t)T * TOT);
     if (e == cudaSuccess) e = dalloc((void**)&h->tot_partial, sizeof(double) * (size_t)T * h->NS * TOT);
     if (e == cudaSuccess) e = dalloc((void**)&h->progress, sizeof(int) * T);
     if (e == cudaSuccess) e = dalloc((void**)&h->abort_flag, sizeof(int));
+    if (e == cudaSuccess) e = dalloc((void**)&h->sym_flag, sizeof(int));
     const size_t nunits = (size_t)((n + TAME_SB - 1) / TAME_SB) * ((T + 31) / 32);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_counter, sizeof(int));
     if (e == cudaSuccess) e = dalloc((void**)&h->dbg, sizeof(unsigned long long) * 16);
     if (e == cudaSuccess) e = dalloc((void**)&h->hand, sizeof(double2) * (size_t)n * T * d);
-    if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits);
+    if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits * h->nparts);
     if (e == cudaSuccess) e = dalloc((void**)&h->red6, sizeof(double) * 6);
     if (e == cudaSuccess) e = dalloc((void**)&h->out6, sizeof(double) * 6);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out6_pinned, sizeof(double) * 6);
@@ -358,7 +379,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     CK(cudaMemset(h->unit_counter, 0, sizeof(int)));
     CK(cudaMemset(h->dbg, 0, sizeof(unsigned long long) * 16));
     CK(cudaMemset(h->hand, 0, sizeof(double2) * (size_t)n * T * d));
-    CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits));
+    CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits * h->nparts));
     {
         const char* v = getenv("TAME_SWEEP");   // "panel" forces the stream-ordered per-panel path (debug / comparison)
         h->fused = (world == 1) && !(v && strcmp(v, "panel") == 0);
@@ -370,7 +391,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
-    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg;
+    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.nparts = h->nparts;
 
     h->nb_ll = h->ops->llmse_blocks(P);
     h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
@@ -387,7 +408,7 @@ int tame_destroy(tame_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : {(void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
-                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg})
+                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->sym_flag})
         if (p) cudaFree(p);
     if (h->out6_pinned) cudaFreeHost(h->out6_pinned);
     if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
@@ -416,6 +437,18 @@ int tame_bind_Y(tame_handle* h, const double* Y) {
     k_hab<<<grid, block, 0, h->stream>>>(h->P);
     tame_count_launch(1);
     CK(cudaGetLastError());
+    // mirror property of Y (single GPU): lets the ELBO/MSE pass stream only the i<j half.  TAME_SYMMETRIC=0 disables.
+    h->y_symmetric = false;
+    const char* sv = getenv("TAME_SYMMETRIC");
+    if (h->P.world == 1 && !(sv && atoi(sv) == 0)) {
+        CK(cudaMemsetAsync(h->sym_flag, 0, sizeof(int), h->stream));
+        k_symcheck<<<grid, block, 0, h->stream>>>(h->P, h->sym_flag);
+        tame_count_launch(1);
+        int bad = 1;
+        CK(cudaMemcpyAsync(&bad, h->sym_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->y_symmetric = (bad == 0);
+    }
     h->y_bound = true;
     return TAME_OK;
 }
@@ -498,7 +531,7 @@ int tame_elbo_mse(tame_handle* h, double* out6_host) {
     cudaStream_t st = h->stream;
     int nb = 0;
     ev_mark(h, 3);
-    h->ops->llmse(P, h->part_ll, &nb, st);
+    h->ops->llmse(P, h->part_ll, &nb, h->y_symmetric ? 1 : 0, st);
     ev_mark(h, 0);
     h->ops->cellterms(P, h->cfg.logdet_S0, h->cfg.logdet_Q, h->part_cell, h->nb_cell, st);
     k_reduce6<<<1, 256, 0, st>>>(h->part_ll, nb, h->part_cell, h->nb_cell, h->red6);

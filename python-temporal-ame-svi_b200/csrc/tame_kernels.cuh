@@ -29,6 +29,7 @@
 #define TAME_CHAIN_WPC 4     // warps (time steps) per chain CTA: one per SM sub-partition, no issue/FP64 contention
 #define TAME_SPIN_LIMIT (1 << 24)
 #define TAME_SB 32           // sub-block of the fused sweep: rows per streaming unit, push granularity
+#define TAME_MAX_PARTS 4     // column parts per streaming unit (k_sweep): 1..TAME_MAX_PARTS
 #define TAME_REFRESH 32      // the chain re-inverts the precision from scratch every TAME_REFRESH nodes (rank-2 updates between)
 
 struct TameParams {
@@ -49,6 +50,7 @@ struct TameParams {
     int* unit_counter;        // next (sub-block, t-slice) unit to hand to a streaming CTA
     int* unit_done;           // (nsb * nslices) epoch stamp written when a unit's H rows are complete
     int epoch;                // sweep number (stamps are compared against it; never reset)
+    int nparts;               // column parts per streaming unit (H holds nparts slabs of nloc*T*2R partial sums)
     int n_chain_ctas;
 };
 
@@ -540,22 +542,34 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             // the static partner part H of this sub-block comes from a streaming CTA of the same launch
             const long long c0 = clock64();
             if (lane == 0) {
-                const int* flag = P.unit_done + (i / TAME_SB) * nslices + (t >> 5);
+                const int* flag = P.unit_done + ((i / TAME_SB) * nslices + (t >> 5)) * P.nparts;
                 int spins = 0;
-                while (tame_ld_acquire(flag) != P.epoch) {
-                    if (++spins > TAME_SPIN_LIMIT) { atomicExch(P.abort_flag, 1); break; }
-                    if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+                for (int part = 0; part < P.nparts; ++part) {
+                    while (tame_ld_acquire(flag + part) != P.epoch) {
+                        if (++spins > TAME_SPIN_LIMIT) { atomicExch(P.abort_flag, 1); break; }
+                        if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+                    }
                 }
             }
             __syncwarp();
             wait_unit += clock64() - c0;
             if (probe && i == 0) dbg[1] = tame_globaltimer();
         }
-        double hb = 0.0;
+        double hb = 0.0, hbp[TAME_MAX_PARTS - 1];
+#pragma unroll
+        for (int part = 0; part < TAME_MAX_PARTS - 1; ++part) hbp[part] = 0.0;
         {
             const int l = tame_lrow(i, P.panel, P.world);
             if (c < 2) hb = P.hab[((size_t)l * T + t) * 2 + c];
-            else if (c < D) hb = __ldcg(P.H + ((size_t)l * T + t) * NV + (c - 2));
+            else if (c < D) {
+                const size_t slab = (size_t)P.nloc * T * NV;
+                const double* hp = P.H + ((size_t)l * T + t) * NV + (c - 2);
+                hb = __ldcg(hp);
+                if (FUSED) {        // the other column parts' partial sums: independent loads, added where h is assembled
+#pragma unroll
+                    for (int part = 1; part < TAME_MAX_PARTS; ++part) hbp[part - 1] = (part < P.nparts) ? __ldcg(hp + part * slab) : 0.0;
+                }
+            }
         }
         const int wlo = window_lo(i);
 
@@ -703,6 +717,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 #pragma unroll
                 for (int k = (D / 3) * 3; k < D; ++k) n0 = fma(cstPQ[cc * D + k], sm.mnext[k], n0);
             }
+            if (FUSED) hb += (hbp[0] + hbp[1]) + hbp[2];
             hval = hb + ((c >= 2 && c < D) ? sm.hin[c - 2] : 0.0);
             hval += (p0 + p1) + p2;          // Qinv Phi mu_{t-1}      (structured_mf.py:258)
             hval += (n0 + n1) + n2;          // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
@@ -809,14 +824,15 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
     constexpr int NV = 2 * R, JC = TameStream<R, RW>::JC;
     __shared__ int s_val;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nslices = (P.T + 31) / 32, nsb = (P.n + TAME_SB - 1) / TAME_SB, nunits = nsb * nslices;
+    const int nslices = (P.T + 31) / 32, nsb = (P.n + TAME_SB - 1) / TAME_SB, nunits = nsb * nslices * P.nparts;
     for (;;) {
         if (tid == 0) s_val = atomicAdd(P.unit_counter, 1);
         __syncthreads();
         const int u = s_val;
         __syncthreads();
         if (u >= nunits) break;
-        const int sb = u / nslices, slice = u - sb * nslices;
+        const int part = u % P.nparts, us = u / P.nparts;            // unit = (sub-block, time slice, column part)
+        const int sb = us / nslices, slice = us - sb * nslices;
         const int kbase = sb * TAME_SB, kw = kbase + warp * RW;
         const int t0 = slice * 32, t = t0 + lane;
         const bool tv = t < P.T;
@@ -833,10 +849,15 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
             rv[rr] = (k < P.n) && tv;
             yrow[rr] = P.Y + ((size_t)min(k, P.n - 1) * P.n * P.T + (tv ? t : 0)) * 2;
         }
-        // (a) static upper part
-        tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, ((kbase + 1) / JC) * JC, P.n, true, accA, accB);
-        // (b) lower columns, released by the chain
-        const int lowend = max(0, (sb - 2) * TAME_SB);
+        // (a) static upper part: this part's share of the columns j > k
+        {
+            const int ub = ((kbase + 1) / JC) * JC;
+            const int len = (((P.n - ub + P.nparts - 1) / P.nparts + JC - 1) / JC) * JC;
+            const int jb = ub + part * len, je = min(P.n, jb + len);
+            tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, jb, je, true, accA, accB);
+        }
+        // (b) lower columns, released by the chain (carried by part 0)
+        const int lowend = (part == 0) ? max(0, (sb - 2) * TAME_SB) : 0;
         int done_cols = 0, spins = 0;
         bool dead = false;
         while (done_cols < lowend && !dead) {
@@ -865,7 +886,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
         for (int rr = 0; rr < RW; ++rr) {
             const int k = kw + rr;
             if (k < P.n && tv) {
-                double* h = P.H + ((size_t)k * P.T + t) * NV;
+                double* h = P.H + (size_t)part * P.nloc * P.T * NV + ((size_t)k * P.T + t) * NV;
 #pragma unroll
                 for (int a = 0; a < R; ++a) {
                     __stcg(h + a, accA[rr][a]);
@@ -887,14 +908,20 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
 // Same streaming tile as k_contract (TameStream).  grid (ceil(T/32), ceil(nloc/(8*RW))), block 256;
 // partial (grid.y*grid.x, 2).
 // ------------------------------------------------------------------------------------------------------
-template <int R, int RW>
-__global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial) {
+// NW warps x RW rows = 32 rows per CTA; NW = 16, RW = 2 doubles the warps per scheduler (the kernel is issue/latency-bound,
+// ncu: long_scoreboard ~ 0, 'wait' dominant at 2 warps per scheduler) at the same ring size.
+// SYM: Y was verified mirror-consistent at bind time (Y[j,i,t,:] == swap(Y[i,j,t,:]) bit for bit, which the reference's
+// generate_data guarantees, temporal_ame.py:209-216): the residuals of (j,i) are those of (i,j) swapped, so the pass only
+// streams the partners j > i and doubles the squared error.  Otherwise the full pass runs.
+template <int R, int RW, int NW, bool SYM>
+__global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* partial) {
     using TS = TameStream<R, RW>;
-    constexpr int D = TS::D, JC = TS::JC, PD = TS::PD, RS = TS::RS, RT = 8 * RW;
+    constexpr int D = TS::D, JC = TS::JC, PD = TS::PD, RS = TS::RS, RT = NW * RW, NT = NW * 32;
+    static_assert(NW * RW == 32, "32-row tile");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 (*Yr)[RW][256] = reinterpret_cast<double2 (*)[RW][256]>(smem_raw);
-    double (*Mb)[JC][32][RS] = reinterpret_cast<double (*)[JC][32][RS]>(smem_raw + TS::Y_BYTES);
-    __shared__ double red[2][8];
+    double2 (*Yr)[RW][NT] = reinterpret_cast<double2 (*)[RW][NT]>(smem_raw);
+    double (*Mb)[JC][32][RS] = reinterpret_cast<double (*)[JC][32][RS]>(smem_raw + (size_t)PD * RW * NT * sizeof(double2));
+    __shared__ double red[2][NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = blockIdx.x * 32, t = t0 + lane;
     const bool tv = t < P.T;
@@ -929,12 +956,12 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
     auto issue_y = [&](int j, int slot) {
 #pragma unroll
         for (int rr = 0; rr < RW; ++rr) {
-            const bool ok = rv[rr] && (j < P.n) && (j != gi[rr]);
+            const bool ok = rv[rr] && (j < P.n) && (SYM ? (j > gi[rr]) : (j != gi[rr]));
             tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
         }
     };
     auto issue_m = [&](int buf, int jc) {
-        for (int e = tid; e < JC * 32 * TS::PIECES; e += 256) {
+        for (int e = tid; e < JC * 32 * TS::PIECES; e += NT) {
             const int piece = e % TS::PIECES, tl = (e / TS::PIECES) & 31, jj = e / (TS::PIECES * 32);
             const int j = jc + jj, tt = t0 + tl;
             const bool ok = (j < P.n) && (tt < P.T);
@@ -942,15 +969,16 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
             tame_cp_async16(&Mb[buf][jj][tl][piece * 2], src, ok);
         }
     };
-    const int nchunks = (P.n + JC - 1) / JC;
-    issue_m(0, 0);
+    const int jbeg = SYM ? (gfirst / JC) * JC : 0;                  // SYM: partners below the tile are never needed
+    const int nchunks = (P.n - jbeg + JC - 1) / JC;
+    issue_m(0, jbeg);
 #pragma unroll
     for (int s = 0; s < PD; ++s) {
-        issue_y(s, s);
+        issue_y(jbeg + s, s);
         tame_cp_async_commit();
     }
     for (int c = 0; c < nchunks; ++c) {
-        const int jc = c * JC, buf = c & 1;
+        const int jc = jbeg + c * JC, buf = c & 1;
         // chunk-uniform case: 0 all partners below the tile's rows, 1 all above, 2 touches the tile's own nodes / the tail
         const int kind = (jc + JC <= gfirst) ? 0 : ((jc > gfirst + RT - 1 && jc + JC <= P.n) ? 1 : 2);
 #pragma unroll
@@ -991,7 +1019,7 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
                         S00[rr] = fma(e0, e0, S00[rr]);
                         S01[rr] = fma(e0, e1, S01[rr]);
                         S11[rr] = fma(e1, e1, S11[rr]);
-                    } else {
+                    } else if (!SYM) {
                         SL[rr] = fma(e0, e0, SL[rr]);
                         SL[rr] = fma(e1, e1, SL[rr]);
                     }
@@ -1006,7 +1034,7 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
 #pragma unroll
     for (int rr = 0; rr < RW; ++rr) {
         if (rv[rr]) {
-            sq += (S00[rr] + S11[rr]) + SL[rr];
+            sq += SYM ? 2.0 * (S00[rr] + S11[rr]) : (S00[rr] + S11[rr]) + SL[rr];
             quad += P.p0 * S00[rr] + 2.0 * P.q * S01[rr] + P.p1 * S11[rr];
         }
     }
@@ -1020,7 +1048,7 @@ __global__ void __launch_bounds__(256, 1) k_llmse(TameParams P, double* partial)
     if (threadIdx.x == 0) {
         double s = 0.0, qd = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { s += red[0][w]; qd += red[1][w]; }
+        for (int w = 0; w < NW; ++w) { s += red[0][w]; qd += red[1][w]; }
         size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
         partial[b * 2 + 0] = s;
         partial[b * 2 + 1] = qd;
@@ -1133,7 +1161,7 @@ struct TameOps {
     cudaError_t (*sweep_fused)(const TameParams&, cudaStream_t);
     int (*sweep_capacity)();
     int (*chain_max_T)();
-    void (*llmse)(const TameParams&, double* partial, int* nblocks, cudaStream_t);
+    void (*llmse)(const TameParams&, double* partial, int* nblocks, int symmetric, cudaStream_t);
     void (*cellterms)(const TameParams&, double logdetS0, double logdetQ, double* partial, int nblocks, cudaStream_t);
     int (*llmse_blocks)(const TameParams&);
 };

@@ -63,7 +63,7 @@ cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
     if (capacity < 0) capacity = sweep_capacity();
     TameParams p = P;
     p.n_chain_ctas = (P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC;
-    const int nunits = ((P.n + TAME_SB - 1) / TAME_SB) * ((P.T + 31) / 32);
+    const int nunits = ((P.n + TAME_SB - 1) / TAME_SB) * ((P.T + 31) / 32) * P.nparts;
     const int workers = capacity - p.n_chain_ctas < nunits ? capacity - p.n_chain_ctas : nunits;
     if (workers < 1) return cudaErrorLaunchOutOfResources;
     void* args[] = {(void*)&p};
@@ -80,17 +80,21 @@ int chain_max_T() {
     return sms * per * TAME_CHAIN_WPC;
 }
 
-int llmse_blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 8 * RW - 1) / (8 * RW)); }
+constexpr int LL_RW = 2, LL_NW = 16;      // k_llmse tile: 16 warps x 2 rows
+int llmse_blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 31) / 32); }
 
-void launch_llmse(const TameParams& P, double* partial, int* nblocks, cudaStream_t st) {
-    dim3 grid((P.T + 31) / 32, (P.nloc + 8 * RW - 1) / (8 * RW));
-    constexpr size_t smem = TameStream<R, RW>::SMEM;
+void launch_llmse(const TameParams& P, double* partial, int* nblocks, int symmetric, cudaStream_t st) {
+    dim3 grid((P.T + 31) / 32, (P.nloc + 31) / 32);
+    constexpr size_t smem = TameStream<R, RW>::SMEM;      // ring PD x LL_RW x 512 x 16 B == PD x RW x 256 x 16 B
+    static_assert(LL_RW * LL_NW == RW * 8, "same ring footprint");
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_llmse<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_llmse<R, LL_RW, LL_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_llmse<R, LL_RW, LL_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    k_llmse<R, RW><<<grid, 256, smem, st>>>(P, partial);
+    if (symmetric) k_llmse<R, LL_RW, LL_NW, true><<<grid, LL_NW * 32, smem, st>>>(P, partial);
+    else k_llmse<R, LL_RW, LL_NW, false><<<grid, LL_NW * 32, smem, st>>>(P, partial);
     *nblocks = grid.x * grid.y;
     tame_count_launch(1);
 }

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtame_b200.so")
+LIB_PATH = os.environ.get("TAME_LIB") or os.path.join(_HERE, "libtame_b200.so")   # TAME_LIB: A/B builds
 
 MODE_NAIVE, MODE_GOOD, MODE_BAD = 0, 1, 2
 MAX_R = 8
