@@ -99,6 +99,7 @@ struct tame_handle {
     cudaStream_t stream = nullptr;
     bool y_bound = false, state_bound = false, y_symmetric = false;
     int* sym_flag = nullptr;
+    int* cursor = nullptr;
     // device scratch
     double *H = nullptr, *hab = nullptr, *tot = nullptr, *tot_partial = nullptr, *cst = nullptr;
     double *part_ll = nullptr, *part_cell = nullptr, *red6 = nullptr, *out6 = nullptr;
@@ -363,6 +364,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     if (e == cudaSuccess) e = dalloc((void**)&h->progress, sizeof(int) * T);
     if (e == cudaSuccess) e = dalloc((void**)&h->abort_flag, sizeof(int));
     if (e == cudaSuccess) e = dalloc((void**)&h->sym_flag, sizeof(int));
+    if (e == cudaSuccess) e = dalloc((void**)&h->cursor, sizeof(int) * TAME_MAX_PARTS);
     const size_t nunits = (size_t)((n + TAME_SB - 1) / TAME_SB) * ((T + 31) / 32);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_counter, sizeof(int));
     if (e == cudaSuccess) e = dalloc((void**)&h->dbg, sizeof(unsigned long long) * 16);
@@ -377,6 +379,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     CK(cudaMemset(h->progress, 0, sizeof(int) * T));
     CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
     CK(cudaMemset(h->unit_counter, 0, sizeof(int)));
+    CK(cudaMemset(h->cursor, 0, sizeof(int) * TAME_MAX_PARTS));
     CK(cudaMemset(h->dbg, 0, sizeof(unsigned long long) * 16));
     CK(cudaMemset(h->hand, 0, sizeof(double2) * (size_t)n * T * d));
     CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits * h->nparts));
@@ -391,7 +394,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
-    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.nparts = h->nparts;
+    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.nparts = h->nparts; P.cursor = h->cursor;
 
     h->nb_ll = h->ops->llmse_blocks(P);
     h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
@@ -408,7 +411,7 @@ int tame_destroy(tame_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : {(void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
-                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->sym_flag})
+                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->sym_flag, (void*)h->cursor})
         if (p) cudaFree(p);
     if (h->out6_pinned) cudaFreeHost(h->out6_pinned);
     if (h->abort_pinned) cudaFreeHost(h->abort_pinned);

@@ -50,6 +50,7 @@ struct TameParams {
     int* unit_counter;        // next (sub-block, t-slice) unit to hand to a streaming CTA
     int* unit_done;           // (nsb * nslices) epoch stamp written when a unit's H rows are complete
     int epoch;                // sweep number (stamps are compared against it; never reset)
+    int* cursor;              // (TAME_MAX_PARTS) column position last published by a streaming CTA of each column part
     int nparts;               // column parts per streaming unit (H holds nparts slabs of nloc*T*2R partial sums)
     int n_chain_ctas;
 };
@@ -190,7 +191,7 @@ struct TameStream {
 template <int R, int RW>
 __device__ __forceinline__ void tame_stream_cols(const TameParams& P, unsigned char* smem_raw, const double* const (&yrow)[RW],
                                                  const bool (&rv)[RW], int kw, int t0, int jb, int je, bool tri,
-                                                 double (&accA)[RW][R], double (&accB)[RW][R]) {
+                                                 double (&accA)[RW][R], double (&accB)[RW][R], int* cursor = nullptr) {
     using TS = TameStream<R, RW>;
     constexpr int D = TS::D, JC = TS::JC, PD = TS::PD, RS = TS::RS;
     static_assert(JC == PD, "ring slot == position in chunk");
@@ -234,6 +235,7 @@ __device__ __forceinline__ void tame_stream_cols(const TameParams& P, unsigned c
             if (jj == 0) {
                 __syncthreads();                               // chunk c's partner records are visible to the CTA
                 if (c + 1 < nchunks) issue_m(buf ^ 1, jc + JC);
+                if (cursor != nullptr && (c & 15) == 0 && tid == 0) *((volatile int*)cursor) = jc;   // convoy position
             }
             double w0[RW], w1[RW];
 #pragma unroll
@@ -367,6 +369,31 @@ __device__ __forceinline__ double tame_gj_inverse(double (&col)[D], double* rowb
 #pragma unroll
         for (int p = 2; p < D; ++p) col[p - 1] = fma(-rk[p], s, col[p]);
         col[D - 1] = s;
+    }
+    return logdet;
+}
+
+// logdet of a symmetric positive-definite DxD matrix (lane c holds column c): forward elimination only -- at step k just
+// the rows below the pivot are updated (half the work of the inverse) -- and the pivots are multiplied in groups of four
+// so that 18 pivots cost 5 logarithms.  rowb: 2*(D+32) doubles.
+template <int D>
+__device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rowb, int lane) {
+    constexpr int RB = D + 32;
+    const int slot = (lane < D) ? lane : D + (lane - D);
+    double logdet = 0.0, prod = 1.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double* rb = rowb + (k & 1) * RB;
+        rb[slot] = col[k];
+        __syncwarp();
+        const double pivv = rb[k];
+        prod *= pivv;
+        if ((k & 3) == 3 || k == D - 1) { logdet += log(prod); prod = 1.0; }
+        if (k + 1 < D) {
+            const double s = col[k] * tame_rcp(pivv);
+#pragma unroll
+            for (int r = k + 1; r < D; ++r) col[r] = fma(-rb[r], s, col[r]);
+        }
     }
     return logdet;
 }
@@ -854,7 +881,19 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
             const int ub = ((kbase + 1) / JC) * JC;
             const int len = (((P.n - ub + P.nparts - 1) / P.nparts + JC - 1) / JC) * JC;
             const int jb = ub + part * len, je = min(P.n, jb + len);
-            tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, jb, je, true, accA, accB);
+            // convoy: start where the other streaming CTAs of this column part currently are and wrap around, so that a
+            // partner-record chunk fetched from HBM by one CTA is L2-hot for the rest (the records are re-read by every
+            // row tile: 151 MB at config 4, more than L2 can hold next to the Y stream)
+            int start = jb;
+            if (je - jb > 64 * JC) {
+                if (tid == 0) s_val = *((volatile int*)(P.cursor + part));
+                __syncthreads();
+                const int cur = s_val;
+                __syncthreads();
+                if (cur > jb && cur < je) start = jb + ((cur - jb) / JC) * JC;
+            }
+            tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, start, je, true, accA, accB, P.cursor + part);
+            if (start > jb) tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, jb, start, true, accA, accB, P.cursor + part);
         }
         // (b) lower columns, released by the chain (carried by part 0)
         const int lowend = (part == 0) ? max(0, (sb - 2) * TAME_SB) : 0;
@@ -1122,7 +1161,7 @@ __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0
             for (int k = 0; k < D; ++k) a = fma(A[c * D + k], vec[warp][k], a);
             quad = resid * a;
         }
-        const double logdet = tame_gj_inverse<D, true>(col, rowb[warp], lane);
+        const double logdet = tame_logdet_spd<D>(col, rowb[warp], lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             tr += __shfl_xor_sync(0xffffffffu, tr, o);
