@@ -528,27 +528,6 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     auto window_lo = [&](int i) { return max(0, (i / WSB - WBACK) * WSB); };
     const int nslices = (T + 31) / 32;
 
-    // static partner part H (+ hab) of node i for this lane's component; the column parts are independent loads
-    auto load_hb = [&](int i, double& hb, double (&hbp)[TAME_MAX_PARTS - 1]) {
-        const int l = tame_lrow(i, P.panel, P.world);
-        hb = 0.0;
-#pragma unroll
-        for (int part = 0; part < TAME_MAX_PARTS - 1; ++part) hbp[part] = 0.0;
-        if (c < 2) hb = P.hab[((size_t)l * T + t) * 2 + c];
-        else if (c < D) {
-            const size_t slab = (size_t)P.nloc * T * NV;
-            const double* hp = P.H + ((size_t)l * T + t) * NV + (c - 2);
-            hb = __ldcg(hp);
-            if (FUSED) {
-#pragma unroll
-                for (int part = 1; part < TAME_MAX_PARTS; ++part) hbp[part - 1] = (part < P.nparts) ? __ldcg(hp + part * slab) : 0.0;
-            }
-        }
-    };
-    double hb_next = 0.0, hbp_next[TAME_MAX_PARTS - 1];
-#pragma unroll
-    for (int part = 0; part < TAME_MAX_PARTS - 1; ++part) hbp_next[part] = 0.0;
-
     // prefetch registers for node i
     double2 yv[NWS];
     double mold = 0.0, mnext = 0.0;
@@ -570,7 +549,6 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             mold = tame_ld_cg(P.Xm + ((size_t)i * T + t) * D + c);
             mnext = has_next ? tame_ld_cg(P.Xm + ((size_t)i * T + t + 1) * D + c) : 0.0;
         }
-        if (!FUSED || (i % TAME_SB) != 0) load_hb(i, hb_next, hbp_next);
     };
     prefetch(i0);
     const bool probe = FUSED && lane == 0 && (t == 0 || t == T - 1);     // timing probes (dbg[0..7]: t=0, [8..15]: t=T-1)
@@ -584,15 +562,6 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 #pragma unroll
         for (int s = 0; s < NWS; ++s) ycur[s] = yv[s];
         const double mo = mold, mn = mnext;
-        // first look at the hand-over slot of (i, t-1): issued now, checked after the inverse (a full L2 round trip later)
-        double2 hv = make_double2(0.0, 0.0);
-        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
-        // static partner part of node i: prefetched with node i-1 unless i opens a sub-block (its unit must be stamped first)
-        double hb = hb_next;
-        double hbp[TAME_MAX_PARTS - 1];
-#pragma unroll
-        for (int part = 0; part < TAME_MAX_PARTS - 1; ++part) hbp[part] = hbp_next[part];
-        const bool hb_ready = (!FUSED || (i % TAME_SB) != 0) && i != i0;
         if (i + 1 < i1) prefetch(i + 1);
         // (hand-over of (i, t-1): the slot carries {mean, tag}; tag ^ bits(mean) == magic proves the 16-byte slot is this
         //  sweep's and untorn -- see "first look" below.)
@@ -613,7 +582,22 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             wait_unit += clock64() - c0;
             if (probe && i == 0) dbg[1] = tame_globaltimer();
         }
-        if (!hb_ready) load_hb(i, hb, hbp);
+        double hb = 0.0, hbp[TAME_MAX_PARTS - 1];
+#pragma unroll
+        for (int part = 0; part < TAME_MAX_PARTS - 1; ++part) hbp[part] = 0.0;
+        {
+            const int l = tame_lrow(i, P.panel, P.world);
+            if (c < 2) hb = P.hab[((size_t)l * T + t) * 2 + c];
+            else if (c < D) {
+                const size_t slab = (size_t)P.nloc * T * NV;
+                const double* hp = P.H + ((size_t)l * T + t) * NV + (c - 2);
+                hb = __ldcg(hp);
+                if (FUSED) {        // the other column parts' partial sums: independent loads, added where h is assembled
+#pragma unroll
+                    for (int part = 1; part < TAME_MAX_PARTS; ++part) hbp[part - 1] = (part < P.nparts) ? __ldcg(hp + part * slab) : 0.0;
+                }
+            }
+        }
         const int wlo = window_lo(i);
 
         if (c < D) { sm.mold[c] = mo; sm.mnext[c] = mn; }
@@ -671,6 +655,10 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             if (lane < NV) sm.hin[lane] = acc;
         }
+
+        // ---- first look at the hand-over slot of (i, t-1); it is checked after the inverse
+        double2 hv = make_double2(0.0, 0.0);
+        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
 
         // ---- inverse of the precision.  P_i = P_{i-1} + G(z_{i-1}^new) - G(z_i^old) with G(z) = J_z' R^-1 J_z of rank 2, so
         // between refreshes the carried raw inverse cw[] follows by two rank-2 (Woodbury) corrections, each with a 2x2
