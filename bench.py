@@ -305,6 +305,15 @@ def run_ours(args, shape):
         dist.broadcast(idbuf, 0)
         raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
         _lib.check(lib.tame_comm_init(h, raw))
+        if os.environ.get("TAME_SWEEP") != "panel":
+            # fused multi-GPU sweep: exchange the CUDA IPC handles of the hand-over buffers
+            mine = (C.c_ubyte * 64)()
+            _lib.check(lib.tame_ipc_export(h, mine))
+            table = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(table, torch.tensor(list(mine), dtype=torch.uint8, device=dev))
+            flat = torch.cat(table).cpu().tolist()
+            _lib.check(lib.tame_ipc_import(h, (C.c_ubyte * (64 * world))(*flat)))
+            dist.barrier()
     _lib.check(lib.tame_bind_Y(h, Y.data_ptr()))
     _lib.check(lib.tame_bind_state(h, Xm.data_ptr(), Xc.data_ptr()))
     _lib.check(lib.tame_set_timing(h, 1))
@@ -391,7 +400,7 @@ def run_ours(args, shape):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (device Philox generator, same distribution as generate_data)",
-            "config": {"workload": workload, "n": n, "T": T, "r": r, "method": "good", "lr": LR, "parallelism": f"node-sharded x{world} (64-node panels, cyclic)",
+            "config": {"workload": workload, "n": n, "T": T, "r": r, "method": "good", "lr": LR, "parallelism": f"node-sharded x{world} (64-node panels, cyclic" + (")" if world == 1 else (", panel scheduler + NCCL broadcasts)" if os.environ.get("TAME_SWEEP") == "panel" else ", fused sweep with NVLink peer hand-over)")),
                        "l2": f"inputs larger than L2: each step streams Y twice ({2 * 16.0 * units / world / 1e9:.1f} GB per GPU per step)"},
             "roofline": {"kernel": ("k_sweep (persistent fused Gauss-Seidel sweep: streaming CTAs contract Y with the partner means while the chain CTAs walk the nodes)"
                                     if fused else "k_contract (partner contraction of the sweep: static upper part + right-looking pushes, summed over its launches in one step)"),

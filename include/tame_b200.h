@@ -139,6 +139,13 @@ int tame_generate_Y(int32_t n, int32_t T, int32_t r, const double R[4], const do
  * owner and tame_elbo_mse all-reduces the partial sums. */
 int tame_comm_unique_id(void* id128_host);
 int tame_comm_init(tame_handle* h, const void* id128_host);
+/* Fused multi-GPU sweep: every rank exports the CUDA IPC handle (64 bytes) of its hand-over buffer, the caller
+ * all-gathers the handles (torch.distributed) and every rank imports the world*64-byte table.  After that tame_sweep runs
+ * the persistent kernel on every rank: the owner of a node writes its {new mean, tag} slots straight into the peers'
+ * buffers over NVLink and the peers' time-step warps follow.  Without it the stream-ordered panel scheduler (NCCL
+ * broadcast per 64-node block) is used. */
+int tame_ipc_export(tame_handle* h, void* handle64_host);
+int tame_ipc_import(tame_handle* h, const void* handles_host);
 /* all-gather the X_cov rows (X_mean is already replicated) so every rank holds the full state */
 int tame_gather_state(tame_handle* h);
 

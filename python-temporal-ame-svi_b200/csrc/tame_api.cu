@@ -105,8 +105,10 @@ struct tame_handle {
     double *part_ll = nullptr, *part_cell = nullptr, *red6 = nullptr, *out6 = nullptr;
     int *progress = nullptr, *abort_flag = nullptr, *unit_counter = nullptr, *unit_done = nullptr;
     int epoch = 0, nparts = 1;
-    bool fused = true;
+    bool fused = true, fused_multi = true;
     double2* hand = nullptr;
+    void* peer_base[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // IPC mappings of the peers' hand buffers
+    int npeers = 0;
     unsigned long long* dbg = nullptr;
     int NS = 1, nb_ll = 0, nb_cell = 0;
     double* out6_pinned = nullptr;
@@ -355,7 +357,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = dalloc((void**)&h->cst, sizeof(double) * c.size());
     // column parts per streaming unit: split the (long) upper part so that the first sub-blocks are ready early
-    h->nparts = (world == 1 && n >= 2048) ? 4 : 1;
+    h->nparts = (n >= 2048) ? 4 : 1;
     if (const char* v = getenv("TAME_NPARTS")) h->nparts = std::max(1, std::min(TAME_MAX_PARTS, atoi(v)));
     if (e == cudaSuccess) e = dalloc((void**)&h->H, sizeof(double) * (size_t)nloc * T * 2 * cfg->r * h->nparts);
     if (e == cudaSuccess) e = dalloc((void**)&h->hab, sizeof(double) * (size_t)nloc * T * 2);
@@ -386,6 +388,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     {
         const char* v = getenv("TAME_SWEEP");   // "panel" forces the stream-ordered per-panel path (debug / comparison)
         h->fused = (world == 1) && !(v && strcmp(v, "panel") == 0);
+        h->fused_multi = !(v && strcmp(v, "panel") == 0);
         if (h->fused && (T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC + 1 > h->ops->sweep_capacity()) h->fused = false;
     }
 
@@ -394,7 +397,9 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
-    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.nparts = h->nparts; P.cursor = h->cursor;
+    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.nparts = h->nparts; P.cursor = h->cursor; P.npeers = 0;
+    for (int k = 0; k < 7; ++k) P.hand_peer[k] = nullptr;
+    CK(cudaDeviceSynchronize());      // the zeroed hand-over slots must be in place before any peer can write into them
 
     h->nb_ll = h->ops->llmse_blocks(P);
     h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
@@ -409,6 +414,7 @@ int tame_destroy(tame_handle* h) {
     if (!h) return TAME_OK;
     cudaSetDevice(h->cfg.device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int k = 0; k < h->npeers; ++k) if (h->peer_base[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
     for (void* p : {(void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
                     (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->sym_flag, (void*)h->cursor})
@@ -487,7 +493,7 @@ int tame_sweep(tame_handle* h) {
     ops->totals(P, h->tot_partial, h->NS, st);
     ev_mark(h, 1);
     h->P.epoch = ++h->epoch;   // stamps of this sweep (hand-over tags, unit_done)
-    if (h->fused) {
+    if (h->fused || (world > 1 && h->npeers == world - 1 && h->fused_multi)) {
         // single GPU: the whole sweep is one persistent cooperative launch (chain CTAs + streaming CTAs)
         ev_mark(h, 2);
         cudaError_t e = ops->sweep_fused(h->P, st);
@@ -721,6 +727,37 @@ int tame_comm_init(tame_handle* h, const void* id128) {
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     NK(g_nccl.CommInitRank(&h->comm, h->P.world, id, h->P.rank));
+    return TAME_OK;
+}
+
+int tame_ipc_export(tame_handle* h, void* handle64_host) {
+    if (!h || !handle64_host) return fail(TAME_EINVAL, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->hand));
+    memcpy(handle64_host, &mh, 64);
+    return TAME_OK;
+}
+
+int tame_ipc_import(tame_handle* h, const void* handles_host) {
+    if (!h || !handles_host) return fail(TAME_EINVAL, "null argument");
+    if (h->P.world == 1) return TAME_OK;
+    if (h->P.world > 8) return fail(TAME_EINVAL, "the fused multi-GPU sweep supports up to 8 ranks");
+    CK(cudaSetDevice(h->cfg.device));
+    int k = 0;
+    for (int r = 0; r < h->P.world; ++r) {
+        if (r == h->P.rank) continue;
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char*)handles_host + 64 * (size_t)r, 64);
+        void* base = nullptr;
+        CK(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_base[k] = base;
+        h->P.hand_peer[k] = (double2*)base;
+        ++k;
+    }
+    h->npeers = k;
+    h->P.npeers = h->fused_multi ? k : 0;
     return TAME_OK;
 }
 

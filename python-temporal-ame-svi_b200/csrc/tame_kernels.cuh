@@ -47,6 +47,8 @@ struct TameParams {
     // fused sweep (k_sweep): work distribution between the chain CTAs and the streaming CTAs
     unsigned long long* dbg;  // 16 timing slots (ns / cycles) written by the first and last time-step warps
     double2* hand;            // (n,T,D) hand-over slots {new mean, tag}: the flag travels with the data
+    double2* hand_peer[7];    // the other ranks' `hand` buffers (CUDA IPC peer pointers over NVLink); npeers entries
+    int npeers;               // > 0: fused multi-GPU sweep (owners publish into every peer, the peers follow)
     int* unit_counter;        // next (sub-block, t-slice) unit to hand to a streaming CTA
     int* unit_done;           // (nsb * nslices) epoch stamp written when a unit's H rows are complete
     int epoch;                // sweep number (stamps are compared against it; never reset)
@@ -556,20 +558,61 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     long long wait_unit = 0, wait_hand = 0, t_gj = 0;
     if (probe) dbg[0] = tame_globaltimer();
 
+    bool prefetched = true;           // the registers/ring slots of node i were loaded by prefetch(i)
     for (int i = i0; i < i1; ++i) {
+        if (FUSED && P.npeers > 0 && !tame_owned(i, P.panel, P.world, P.rank)) {
+            // ---- multi-GPU follower: node i belongs to another rank.  Its owner wrote {new mean, tag} straight into this
+            // rank's hand-over slots over NVLink; take it, keep the running moments, the window ring and the replicated
+            // X_mean in step, skip everything else (no inverse, no covariance).
+            double mo_f = 0.0;
+            if (c < D) mo_f = tame_ld_cg(P.Xm + ((size_t)i * T + t) * D + c);
+            double2 hf = make_double2(0.0, 0.0);
+            int spins = 0;
+            for (;;) {
+                if (c < D) hf = tame_ld_volatile2(hand_mine + (size_t)i * T * D);
+                const bool ok = (c >= D) ||
+                    (((unsigned long long)__double_as_longlong(hf.x) ^ (unsigned long long)__double_as_longlong(hf.y)) == magic);
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > TAME_SPIN_LIMIT) { if (lane == 0) atomicExch(P.abort_flag, 1); break; }
+                if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+            }
+            if (c < D) {
+                sm.mold[c] = mo_f;
+                sm.mnew[c] = hf.x;
+                tame_st_cg(P.Xm + ((size_t)i * T + t) * D + c, hf.x);
+            }
+            __syncwarp();
+            tot_update(sm.mold, -1.0);
+            tot_update(sm.mnew, 1.0);
+            if (lane < NV) sm.ring[i & (TAME_RING - 1)][lane] = tame_zof<R>(sm.mnew, lane);
+            if (((i + 1) % TAME_SB) == 0 || i + 1 == i1) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) tame_st_release(P.progress + t, i + 1);
+            }
+            __syncwarp();
+            have_cw = false;          // the carried inverse is rebuilt at the next owned node
+            prefetched = false;
+            continue;
+        }
+        if (!prefetched) {            // first owned node after foreign ones
+            prefetch(i);
+            prefetched = true;
+        }
         // ---- take the prefetched values, start the next node's loads
         double2 ycur[NWS];
 #pragma unroll
         for (int s = 0; s < NWS; ++s) ycur[s] = yv[s];
         const double mo = mold, mn = mnext;
-        if (i + 1 < i1) prefetch(i + 1);
+        const bool next_mine = (i + 1 < i1) && !(FUSED && P.npeers > 0 && !tame_owned(i + 1, P.panel, P.world, P.rank));
+        if (next_mine) prefetch(i + 1); else prefetched = false;
         // (hand-over of (i, t-1): the slot carries {mean, tag}; tag ^ bits(mean) == magic proves the 16-byte slot is this
         //  sweep's and untorn -- see "first look" below.)
         if (FUSED && (i % TAME_SB) == 0) {
             // the static partner part H of this sub-block comes from a streaming CTA of the same launch
             const long long c0 = clock64();
             if (lane == 0) {
-                const int* flag = P.unit_done + ((i / TAME_SB) * nslices + (t >> 5)) * P.nparts;
+                const int* flag = P.unit_done + ((tame_lrow(i, P.panel, P.world) / TAME_SB) * nslices + (t >> 5)) * P.nparts;
                 int spins = 0;
                 for (int part = 0; part < P.nparts; ++part) {
                     while (tame_ld_acquire(flag + part) != P.epoch) {
@@ -766,9 +809,14 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             const double mu = (m0 + m1) + m2;
             const double mnew = lr * mu + om * mo;
             tame_st_cg(P.Xm + ((size_t)i * T + t) * D + c, mnew);
-            if (has_next) {
+            if (has_next || (FUSED && P.npeers > 0)) {
                 const unsigned long long tag = (unsigned long long)__double_as_longlong(mnew) ^ magic;
-                __stcg(hand_mine + (size_t)i * T * D, make_double2(mnew, __longlong_as_double((long long)tag)));
+                const double2 slotv = make_double2(mnew, __longlong_as_double((long long)tag));
+                const size_t off = (size_t)i * T * D + (size_t)t * D + c;
+                __stcg(P.hand + off, slotv);
+                if (FUSED) {
+                    for (int pr = 0; pr < P.npeers; ++pr) __stcg(P.hand_peer[pr] + off, slotv);     // NVLink peer stores
+                }
             }
             sm.mnew[c] = mnew;
         }
@@ -780,7 +828,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         }
 
         // ---- covariance, damped write (coalesced through shared memory)
-        if (i + 1 < i1) tame_cp_async_wait<1>(); else tame_cp_async_wait<0>();   // node i's old covariance has landed
+        if (next_mine) tame_cp_async_wait<1>(); else tame_cp_async_wait<0>();   // node i's old covariance has landed
         if (c < D) {
             if (P.mode == 0) {
                 const double dinv = 1.0 / (pdiag + 1e-8);
@@ -851,7 +899,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
     constexpr int NV = 2 * R, JC = TameStream<R, RW>::JC;
     __shared__ int s_val;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nslices = (P.T + 31) / 32, nsb = (P.n + TAME_SB - 1) / TAME_SB, nunits = nsb * nslices * P.nparts;
+    const int nslices = (P.T + 31) / 32, nsb = (P.nloc + TAME_SB - 1) / TAME_SB, nunits = nsb * nslices * P.nparts;   // local sub-blocks
     for (;;) {
         if (tid == 0) s_val = atomicAdd(P.unit_counter, 1);
         __syncthreads();
@@ -859,8 +907,9 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
         __syncthreads();
         if (u >= nunits) break;
         const int part = u % P.nparts, us = u / P.nparts;            // unit = (sub-block, time slice, column part)
-        const int sb = us / nslices, slice = us - sb * nslices;
-        const int kbase = sb * TAME_SB, kw = kbase + warp * RW;
+        const int lsb = us / nslices, slice = us - lsb * nslices;                 // local sub-block (storage order)
+        const int kbase = tame_grow(lsb * TAME_SB, P.panel, P.world, P.rank);    // its first node
+        const int sb = kbase / TAME_SB, kw = kbase + warp * RW;
         const int t0 = slice * 32, t = t0 + lane;
         const bool tv = t < P.T;
         double accA[RW][R], accB[RW][R];
@@ -874,7 +923,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
         for (int rr = 0; rr < RW; ++rr) {
             const int k = kw + rr;
             rv[rr] = (k < P.n) && tv;
-            yrow[rr] = P.Y + ((size_t)min(k, P.n - 1) * P.n * P.T + (tv ? t : 0)) * 2;
+            yrow[rr] = P.Y + ((size_t)tame_lrow(min(k, P.n - 1), P.panel, P.world) * P.n * P.T + (tv ? t : 0)) * 2;
         }
         // (a) static upper part: this part's share of the columns j > k
         {
@@ -925,7 +974,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
         for (int rr = 0; rr < RW; ++rr) {
             const int k = kw + rr;
             if (k < P.n && tv) {
-                double* h = P.H + (size_t)part * P.nloc * P.T * NV + ((size_t)k * P.T + t) * NV;
+                double* h = P.H + (size_t)part * P.nloc * P.T * NV + ((size_t)tame_lrow(k, P.panel, P.world) * P.T + t) * NV;
 #pragma unroll
                 for (int a = 0; a < R; ++a) {
                     __stcg(h + a, accA[rr][a]);

@@ -56,6 +56,8 @@ SIGNATURES = {
     "tame_generate_Y": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _DP, _P, C.c_uint64, C.c_int32, C.c_int32, _P, _P]),
     "tame_comm_unique_id": (C.c_int, [_P]),
     "tame_comm_init": (C.c_int, [_P, _P]),
+    "tame_ipc_export": (C.c_int, [_P, _P]),
+    "tame_ipc_import": (C.c_int, [_P, _P]),
     "tame_gather_state": (C.c_int, [_P]),
     "tame_last_timing": (C.c_int, [_P, _DP, _DP, _DP, _DP, _DP]),
     "tame_set_timing": (C.c_int, [_P, C.c_int32]),
