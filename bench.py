@@ -44,6 +44,19 @@ def parse_shape(s):
     return n, T, r
 
 
+def measured_traffic(n, T, r, kernel="k_sweep"):
+    """DRAM bytes per launch of the sweep kernel from the committed ncu capture (profiles/r01_traffic.json), when the
+    capture was taken at this configuration; None otherwise."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if (t["n"], t["T"], t["r"]) == (n, T, r):
+            return t[kernel]["dram_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -54,7 +67,8 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons.  Started before the warm-up (nvidia-smi needs a moment to start); only the
+    samples whose wall-clock time falls inside the timed region are reported (all samples if none does)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -65,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -73,19 +87,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = [r for (ts, r) in self.rows if t0 is None or (t0 - 0.02 <= ts <= t1 + 0.08)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for (_, r) in self.rows], "warm-up + timed region"
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for k, nm in enumerate(names):
@@ -94,7 +113,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -324,13 +343,14 @@ def run_ours(args, shape):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        _lib.check(lib.tame_iterate(h, out6))
-    launches0 = lib.tame_launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        _lib.check(lib.tame_iterate(h, out6))
+    launches0 = lib.tame_launch_count()
     barrier()
+    wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kt = np.zeros(5)
     e0.record()
@@ -343,6 +363,7 @@ def run_ours(args, shape):
         kt += np.array([x.value for x in tm])
     e1.record()
     barrier()
+    wall1 = time.time()
     probes = (C.c_uint64 * 16)()
     lib.tame_debug_probes(h, probes)
     probes = list(probes)
@@ -352,7 +373,7 @@ def run_ours(args, shape):
         tms = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     kt /= args.steps   # per-step ms: sweep, elbo, contract, chain, llmse
     units = float(n) * n * T
     value = units * args.steps / (ms * 1e-3)
@@ -405,7 +426,8 @@ def run_ours(args, shape):
             "roofline": {"kernel": ("k_sweep (persistent fused Gauss-Seidel sweep: streaming CTAs contract Y with the partner means while the chain CTAs walk the nodes)"
                                     if fused else "k_contract (partner contraction of the sweep: static upper part + right-looking pushes, summed over its launches in one step)"),
                          "bound": "hbm", "achieved": contract_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": (contract_gbs / peak) if contract_gbs else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (contract_gbs / peak) if contract_gbs else None,
+                         "traffic": measured_traffic(n, T, r) if (fused and world == 1) else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_unit": 16, "units_per_step": units,
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_unit": 32},
                          "kernels_ms_per_step": {"sweep_total": kt[0], "elbo_total": kt[1], "k_contract": kt[2], ("k_sweep" if fused else "k_chain"): kt[3], "k_llmse": kt[4]},
