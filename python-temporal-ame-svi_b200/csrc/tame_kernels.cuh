@@ -412,11 +412,122 @@ struct TameChainSmem {
     double cold[2][D * D + 2];   // old covariance of the current / next node (cp.async double buffer)
     double wbuf[TAME_RING * 2];
     double mold[D], mnew[D], mprev[D], mnext[D], hvec[D], hin[NV];
+    // inputs of node k prepared by the helper warp (double-buffered by node parity)
+    struct Inp { double hin[NV]; double mold[D]; double mnext[D]; double hb[D]; double wlast[2]; };
+    Inp inp[2];
+    int h_ready;                 // last node whose inputs the helper has published
+    int c_done;                  // last node the chain warp has finished (its new z is in the ring)
+    int pad_[2];                 // keep sizeof a multiple of 16 (cp.async destinations of the next warp's block)
 };
+static_assert(sizeof(TameChainSmem<1>) % 16 == 0 && sizeof(TameChainSmem<2>) % 16 == 0 && sizeof(TameChainSmem<3>) % 16 == 0 &&
+              sizeof(TameChainSmem<4>) % 16 == 0 && sizeof(TameChainSmem<8>) % 16 == 0, "per-warp chain block must stay 16-byte aligned");
 
 // z component x of a mean vector held in shared memory
 template <int R>
 __device__ __forceinline__ double tame_zof(const double* m, int x) { return m[tame_zidx<R>(x)]; }
+
+// bounded spin on a shared-memory counter written by the partner warp of the same CTA
+__device__ __forceinline__ void tame_wait_smem(const int* flag, int target, int lane, int* abort_flag) {
+    if (lane == 0) {
+        int spins = 0;
+        while (*((volatile const int*)flag) < target) {
+            if (++spins > TAME_SPIN_LIMIT) { atomicExch(abort_flag, 1); break; }
+            if ((spins & 1023) == 0 && *((volatile int*)abort_flag)) break;
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+
+// Helper warp of time step t (warps 4..7 of a chain CTA): everything of node k that does not sit on the chain's critical
+// path -- the strided loads of the inline window's Y entries, the window's partial sum over the ring (all partners
+// up to k-2; the chain adds partner k-1 itself), the node's old means, the stamp of its streaming unit and the static
+// partner part H -- prepared one to two nodes ahead and handed over through double-buffered shared memory.
+template <int R, bool FUSED>
+__device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChainSmem<R>& sm, int lane, int t, int i0, int i1) {
+    using S = TameChainSmem<R>;
+    constexpr int WSB = FUSED ? TAME_SB : TAME_WIN, WBACK = FUSED ? 2 : 0;
+    constexpr int D = S::D, NV = S::NV, NWS = FUSED ? 3 : 2;
+    const int T = P.T, c = lane;
+    const bool has_next = t < T - 1;
+    const int nslices = (T + 31) / 32;
+    for (int k = i0; k < i1; ++k) {
+        if (FUSED && P.npeers > 0 && !tame_owned(k, P.panel, P.world, P.rank)) continue;   // the chain follows foreign nodes itself
+        const int l = tame_lrow(k, P.panel, P.world);
+        const int wlo = max(0, (k / WSB - WBACK) * WSB), cnt = k - wlo;
+        // loads that do not depend on the chain
+        double2 yv[NWS];
+#pragma unroll
+        for (int s = 0; s < NWS; ++s) {
+            const int j = wlo + lane + 32 * s;
+            yv[s] = (j < k) ? tame_ld_stream2(P.Y + (((size_t)l * P.n + j) * T + t) * 2) : make_double2(0.0, 0.0);
+        }
+        double mo = 0.0, mn = 0.0;
+        if (c < D) {
+            mo = tame_ld_cg(P.Xm + ((size_t)k * T + t) * D + c);
+            mn = has_next ? tame_ld_cg(P.Xm + ((size_t)k * T + t + 1) * D + c) : 0.0;
+        }
+        if (FUSED && (k % TAME_SB) == 0) {
+            // the static partner part H of this sub-block comes from streaming CTAs of the same launch
+            if (lane == 0) {
+                const int* flag = P.unit_done + ((l / TAME_SB) * nslices + (t >> 5)) * P.nparts;
+                int spins = 0;
+                for (int part = 0; part < P.nparts; ++part) {
+                    while (tame_ld_acquire(flag + part) != P.epoch) {
+                        if (++spins > TAME_SPIN_LIMIT) { atomicExch(P.abort_flag, 1); break; }
+                        if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        double hb = 0.0;
+        if (c < 2) hb = P.hab[((size_t)l * T + t) * 2 + c];
+        else if (c < D) {
+            const size_t slab = (size_t)P.nloc * T * NV;
+            const double* hp = P.H + ((size_t)l * T + t) * NV + (c - 2);
+            double part[TAME_MAX_PARTS];
+#pragma unroll
+            for (int pp = 0; pp < TAME_MAX_PARTS; ++pp) part[pp] = (pp < (FUSED ? P.nparts : 1)) ? __ldcg(hp + pp * slab) : 0.0;
+            hb = (part[0] + part[1]) + (part[2] + part[3]);
+        }
+        // the window's weights
+#pragma unroll
+        for (int s = 0; s < NWS; ++s) {
+            const int slot = lane + 32 * s;
+            sm.wbuf[slot * 2 + 0] = P.p0 * yv[s].x + P.q * yv[s].y;
+            sm.wbuf[slot * 2 + 1] = P.q * yv[s].x + P.p1 * yv[s].y;
+        }
+        // the ring must hold every node up to k-2, and the chain must be done with this input buffer (node k-2)
+        if (k - 2 >= i0) tame_wait_smem(&sm.c_done, k - 2, lane, P.abort_flag);
+        else __syncwarp();
+        // partial window sum over the partners wlo .. k-2  (slots 0 .. cnt-2)
+        const int cnt1 = max(cnt - 1, 0);
+        const int x = lane & 15, half = lane >> 4;
+        double acc = 0.0;
+        {
+            const int xx = min(x, NV - 1), wsel = (xx < R) ? 0 : 1;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int jj = half;
+            for (; jj + 6 < cnt1; jj += 8) {
+                a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
+                a1 = fma(sm.wbuf[(jj + 2) * 2 + wsel], sm.ring[(wlo + jj + 2) & (TAME_RING - 1)][xx], a1);
+                a2 = fma(sm.wbuf[(jj + 4) * 2 + wsel], sm.ring[(wlo + jj + 4) & (TAME_RING - 1)][xx], a2);
+                a3 = fma(sm.wbuf[(jj + 6) * 2 + wsel], sm.ring[(wlo + jj + 6) & (TAME_RING - 1)][xx], a3);
+            }
+            for (; jj < cnt1; jj += 2) a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
+            acc = (x < NV) ? (a0 + a1) + (a2 + a3) : 0.0;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        typename S::Inp& in = sm.inp[k & 1];
+        if (lane < NV) in.hin[lane] = acc;
+        if (c < D) { in.mold[c] = mo; in.mnext[c] = mn; in.hb[c] = hb; }
+        if (lane < 2) in.wlast[lane] = (cnt >= 1) ? sm.wbuf[(cnt - 1) * 2 + lane] : 0.0;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *((volatile int*)&sm.h_ready) = k;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------------
 // k_chain: the Gauss-Seidel chain over nodes [i0,i1) (one panel, i1-i0 <= TAME_WIN, owned by this rank).
@@ -437,17 +548,26 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     //                !FUSED -> the current 64-node block only (earlier blocks were pushed by k_contract launches)
     constexpr int WSB = FUSED ? TAME_SB : TAME_WIN;
     constexpr int WBACK = FUSED ? 2 : 0;
-    constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP, NE = (D * D + 31) / 32, NWS = FUSED ? 3 : 2;
+    constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP, NE = (D * D + 31) / 32;
     double* cstQP = reinterpret_cast<double*>(smem_raw);          // QinvPhi   (D*D)
     double* cstPQ = cstQP + D * D;                                // Phi'Qinv  (D*D)
     S* warps = reinterpret_cast<S*>(cstPQ + D * D);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < 2 * D * D; e += blockDim.x) cstQP[e] = P.cst[3 * D * D + e];
+    if (threadIdx.x < TAME_CHAIN_WPC) { warps[threadIdx.x].h_ready = i0 - 1; warps[threadIdx.x].c_done = i0 - 1; }
     __syncthreads();
-    if (warp >= TAME_CHAIN_WPC) return;      // chain CTAs of k_sweep carry 8 warps; only one per sub-partition works
-    const int t = cta * TAME_CHAIN_WPC + warp;
+    // a chain CTA carries 8 warps: warps 0..3 are the chain warps of 4 consecutive time steps (one per SM sub-partition),
+    // warps 4..7 their helpers
+    const bool is_helper = warp >= TAME_CHAIN_WPC;
+    const int wpair = warp - (is_helper ? TAME_CHAIN_WPC : 0);
+    if (wpair >= TAME_CHAIN_WPC) return;
+    const int t = cta * TAME_CHAIN_WPC + wpair;
     if (t >= P.T) return;
-    S& sm = warps[warp];
+    S& sm = warps[wpair];
+    if (is_helper) {
+        tame_chain_helper<R, FUSED>(P, sm, lane, t, i0, i1);
+        return;
+    }
     const int T = P.T;
     const bool has_prev = t > 0, has_next = t < T - 1;
     const int c = lane;   // column / component owned by this lane
@@ -528,29 +648,14 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     const double2* hand_prev = P.hand + (size_t)(t - 1) * D + min(c, D - 1);   // + i*T*D : slot of (i, t-1), lane c
     double2* hand_mine = P.hand + (size_t)t * D + min(c, D - 1);
     auto window_lo = [&](int i) { return max(0, (i / WSB - WBACK) * WSB); };
-    const int nslices = (T + 31) / 32;
 
-    // prefetch registers for node i
-    double2 yv[NWS];
-    double mold = 0.0, mnext = 0.0;
+    // old covariance of node i -> shared (asynchronous 16-byte copies; X_cov blocks are 16-byte aligned); everything else
+    // of the node's inputs comes from the helper warp
     auto prefetch = [&](int i) {
-        const int l = tame_lrow(i, P.panel, P.world);
-        const int wlo = window_lo(i);
-#pragma unroll
-        for (int s = 0; s < NWS; ++s) {
-            int j = wlo + lane + 32 * s;
-            yv[s] = (j < i) ? tame_ld_stream2(P.Y + (((size_t)l * P.n + j) * T + t) * 2) : make_double2(0.0, 0.0);
-        }
-        {   // old covariance of node i -> shared (asynchronous 16-byte copies; X_cov blocks are 16-byte aligned)
-            const double* cp = P.Xc + ((size_t)i * T + t) * D * D;
-            double* dst = sm.cold[i & 1];
-            for (int e = lane; e < (D * D) / 2; e += 32) tame_cp_async16(dst + 2 * e, cp + 2 * e, true);
-            tame_cp_async_commit();
-        }
-        if (c < D) {
-            mold = tame_ld_cg(P.Xm + ((size_t)i * T + t) * D + c);
-            mnext = has_next ? tame_ld_cg(P.Xm + ((size_t)i * T + t + 1) * D + c) : 0.0;
-        }
+        const double* cp = P.Xc + ((size_t)i * T + t) * D * D;
+        double* dst = sm.cold[i & 1];
+        for (int e = lane; e < (D * D) / 2; e += 32) tame_cp_async16(dst + 2 * e, cp + 2 * e, true);
+        tame_cp_async_commit();
     };
     prefetch(i0);
     const bool probe = FUSED && lane == 0 && (t == 0 || t == T - 1);     // timing probes (dbg[0..7]: t=0, [8..15]: t=T-1)
@@ -590,7 +695,9 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
                 __syncwarp();
                 if (lane == 0) tame_st_release(P.progress + t, i + 1);
             }
+            __threadfence_block();
             __syncwarp();
+            if (lane == 0) *((volatile int*)&sm.c_done) = i;
             have_cw = false;          // the carried inverse is rebuilt at the next owned node
             prefetched = false;
             continue;
@@ -599,48 +706,18 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             prefetch(i);
             prefetched = true;
         }
-        // ---- take the prefetched values, start the next node's loads
-        double2 ycur[NWS];
-#pragma unroll
-        for (int s = 0; s < NWS; ++s) ycur[s] = yv[s];
-        const double mo = mold, mn = mnext;
+        // ---- start the next node's covariance copy, then take this node's inputs from the helper warp
         const bool next_mine = (i + 1 < i1) && !(FUSED && P.npeers > 0 && !tame_owned(i + 1, P.panel, P.world, P.rank));
         if (next_mine) prefetch(i + 1); else prefetched = false;
-        // (hand-over of (i, t-1): the slot carries {mean, tag}; tag ^ bits(mean) == magic proves the 16-byte slot is this
-        //  sweep's and untorn -- see "first look" below.)
-        if (FUSED && (i % TAME_SB) == 0) {
-            // the static partner part H of this sub-block comes from a streaming CTA of the same launch
-            const long long c0 = clock64();
-            if (lane == 0) {
-                const int* flag = P.unit_done + ((tame_lrow(i, P.panel, P.world) / TAME_SB) * nslices + (t >> 5)) * P.nparts;
-                int spins = 0;
-                for (int part = 0; part < P.nparts; ++part) {
-                    while (tame_ld_acquire(flag + part) != P.epoch) {
-                        if (++spins > TAME_SPIN_LIMIT) { atomicExch(P.abort_flag, 1); break; }
-                        if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
-                    }
-                }
-            }
-            __syncwarp();
-            wait_unit += clock64() - c0;
-            if (probe && i == 0) dbg[1] = tame_globaltimer();
-        }
-        double hb = 0.0, hbp[TAME_MAX_PARTS - 1];
-#pragma unroll
-        for (int part = 0; part < TAME_MAX_PARTS - 1; ++part) hbp[part] = 0.0;
         {
-            const int l = tame_lrow(i, P.panel, P.world);
-            if (c < 2) hb = P.hab[((size_t)l * T + t) * 2 + c];
-            else if (c < D) {
-                const size_t slab = (size_t)P.nloc * T * NV;
-                const double* hp = P.H + ((size_t)l * T + t) * NV + (c - 2);
-                hb = __ldcg(hp);
-                if (FUSED) {        // the other column parts' partial sums: independent loads, added where h is assembled
-#pragma unroll
-                    for (int part = 1; part < TAME_MAX_PARTS; ++part) hbp[part - 1] = (part < P.nparts) ? __ldcg(hp + part * slab) : 0.0;
-                }
-            }
+            const long long c0 = clock64();
+            tame_wait_smem(&sm.h_ready, i, lane, P.abort_flag);
+            wait_unit += clock64() - c0;
+            if (probe && i == i0) dbg[1] = tame_globaltimer();
         }
+        const typename S::Inp& in = sm.inp[i & 1];
+        const double mo = (c < D) ? in.mold[c] : 0.0, mn = (c < D) ? in.mnext[c] : 0.0;
+        double hb = (c < D) ? in.hb[c] : 0.0;
         const int wlo = window_lo(i);
 
         if (c < D) { sm.mold[c] = mo; sm.mnext[c] = mn; }
@@ -669,34 +746,11 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             }
         }
 
-        // ---- inline window: partners of this panel that were already updated (new means, same time step)
-        {
-#pragma unroll
-            for (int s = 0; s < NWS; ++s) {
-                int slot = lane + 32 * s;
-                sm.wbuf[slot * 2 + 0] = P.p0 * ycur[s].x + P.q * ycur[s].y;
-                sm.wbuf[slot * 2 + 1] = P.q * ycur[s].x + P.p1 * ycur[s].y;
-            }
-            __syncwarp();
-            const int cnt = i - wlo;
-            const int x = lane & 15, half = lane >> 4;
-            double acc = 0.0;
-            {
-                // lane = (component x, parity of the window slot); four independent partial sums per lane
-                const int xx = min(x, NV - 1), wsel = (xx < R) ? 0 : 1;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int jj = half;
-                for (; jj + 6 < cnt; jj += 8) {
-                    a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
-                    a1 = fma(sm.wbuf[(jj + 2) * 2 + wsel], sm.ring[(wlo + jj + 2) & (TAME_RING - 1)][xx], a1);
-                    a2 = fma(sm.wbuf[(jj + 4) * 2 + wsel], sm.ring[(wlo + jj + 4) & (TAME_RING - 1)][xx], a2);
-                    a3 = fma(sm.wbuf[(jj + 6) * 2 + wsel], sm.ring[(wlo + jj + 6) & (TAME_RING - 1)][xx], a3);
-                }
-                for (; jj < cnt; jj += 2) a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
-                acc = (x < NV) ? (a0 + a1) + (a2 + a3) : 0.0;
-            }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            if (lane < NV) sm.hin[lane] = acc;
+        // ---- inline window: the helper summed the partners wlo..i-2; partner i-1 (whose new z this warp wrote last) is added here
+        if (lane < NV) {
+            double acc = in.hin[lane];
+            if (i - wlo >= 1) acc = fma(in.wlast[(lane < R) ? 0 : 1], sm.ring[(i - 1) & (TAME_RING - 1)][lane], acc);
+            sm.hin[lane] = acc;
         }
 
         // ---- first look at the hand-over slot of (i, t-1); it is checked after the inverse
@@ -787,7 +841,6 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 #pragma unroll
                 for (int k = (D / 3) * 3; k < D; ++k) n0 = fma(cstPQ[cc * D + k], sm.mnext[k], n0);
             }
-            if (FUSED) hb += (hbp[0] + hbp[1]) + hbp[2];
             hval = hb + ((c >= 2 && c < D) ? sm.hin[c - 2] : 0.0);
             hval += (p0 + p1) + p2;          // Qinv Phi mu_{t-1}      (structured_mf.py:258)
             hval += (n0 + n1) + n2;          // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
@@ -851,7 +904,9 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
         // ---- totals with the new mean, window ring
         tot_update(sm.mnew, 1.0);
         if (lane < NV) sm.ring[i & (TAME_RING - 1)][lane] = tame_zof<R>(sm.mnew, lane);
+        __threadfence_block();
         __syncwarp();
+        if (lane == 0) *((volatile int*)&sm.c_done) = i;
     }
     if (probe) {
         dbg[2] = tame_globaltimer();
@@ -870,7 +925,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 
 // stand-alone chain launch over one 64-node block (multi-GPU path); cooperative, grid = ceil(T/8)
 template <int R>
-__global__ void __launch_bounds__(TAME_CHAIN_WPC * 32, 1) k_chain(TameParams P, int i0, int i1) {
+__global__ void __launch_bounds__(2 * TAME_CHAIN_WPC * 32, 1) k_chain(TameParams P, int i0, int i1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tame_chain_body<R, false>(P, smem_raw, blockIdx.x, i0, i1);
 }

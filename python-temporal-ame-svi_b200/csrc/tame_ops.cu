@@ -43,7 +43,7 @@ cudaError_t launch_chain(const TameParams& P, int i0, int i1, cudaStream_t st) {
     void* args[] = {(void*)&p, (void*)&i0, (void*)&i1};
     dim3 grid((P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC);
     tame_count_launch(1);
-    return cudaLaunchCooperativeKernel((void*)k_chain<R>, grid, dim3(TAME_CHAIN_WPC * 32), args, smem, st);
+    return cudaLaunchCooperativeKernel((void*)k_chain<R>, grid, dim3(2 * TAME_CHAIN_WPC * 32), args, smem, st);
 }
 
 size_t sweep_smem_bytes() { return chain_smem_bytes() > TameStream<R, RW>::SMEM ? chain_smem_bytes() : TameStream<R, RW>::SMEM; }
@@ -76,7 +76,7 @@ int chain_max_T() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<R>, TAME_CHAIN_WPC * 32, chain_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<R>, 2 * TAME_CHAIN_WPC * 32, chain_smem_bytes());
     return sms * per * TAME_CHAIN_WPC;
 }
 
