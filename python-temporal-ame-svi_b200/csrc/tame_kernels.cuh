@@ -715,6 +715,9 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             wait_unit += clock64() - c0;
             if (probe && i == i0) dbg[1] = tame_globaltimer();
         }
+        // first look at the hand-over slot of (i, t-1): issued now (after the wait on the helper), checked after the inverse
+        double2 hv = make_double2(0.0, 0.0);
+        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
         const typename S::Inp& in = sm.inp[i & 1];
         const double mo = (c < D) ? in.mold[c] : 0.0, mn = (c < D) ? in.mnext[c] : 0.0;
         double hb = (c < D) ? in.hb[c] : 0.0;
@@ -752,10 +755,6 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             if (i - wlo >= 1) acc = fma(in.wlast[(lane < R) ? 0 : 1], sm.ring[(i - 1) & (TAME_RING - 1)][lane], acc);
             sm.hin[lane] = acc;
         }
-
-        // ---- first look at the hand-over slot of (i, t-1); it is checked after the inverse
-        double2 hv = make_double2(0.0, 0.0);
-        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
 
         // ---- inverse of the precision.  P_i = P_{i-1} + G(z_{i-1}^new) - G(z_i^old) with G(z) = J_z' R^-1 J_z of rank 2, so
         // between refreshes the carried raw inverse cw[] follows by two rank-2 (Woodbury) corrections, each with a 2x2
