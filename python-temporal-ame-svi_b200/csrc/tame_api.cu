@@ -221,6 +221,35 @@ __global__ void __launch_bounds__(256) k_symcheck(TameParams P, int* flag) {
     if (bad) *flag = 1;
 }
 
+// Mirror check across ranks: a rank only holds its own rows, so the pair (Y[i,j], Y[j,i]) is split between two ranks.
+// Every entry contributes a signed 64-bit hash of (unordered dyad, t, value as seen from the lower index): +h for i<j,
+// -h of the swapped value for i>j; the wrap-around sum over ALL ranks (NCCL all-reduce) is 0 when every dyad is
+// mirror-consistent and non-zero otherwise, up to a 2^-64 collision probability.  grid (ceil(T/32), nloc), block (32,8).
+__device__ __forceinline__ unsigned long long tame_mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+__global__ void __launch_bounds__(256) k_symhash(TameParams P, unsigned long long* acc) {
+    const int lrow = blockIdx.y;
+    const int i = tame_grow(lrow, P.panel, P.world, P.rank);
+    const int t = blockIdx.x * 32 + threadIdx.x;
+    unsigned long long sum = 0;
+    if (t < P.T) {
+        for (int j = threadIdx.y; j < P.n; j += 8) {
+            if (j == i) continue;
+            const double2 y = tame_ld_stream2(P.Y + (((size_t)lrow * P.n + j) * P.T + t) * 2);
+            const int lo = min(i, j), hi = max(i, j);
+            const unsigned long long key = ((unsigned long long)lo * P.n + hi) * (unsigned long long)P.T + t;
+            const unsigned long long a = (unsigned long long)__double_as_longlong(i < j ? y.x : y.y);   // y_{lo,hi}
+            const unsigned long long b = (unsigned long long)__double_as_longlong(i < j ? y.y : y.x);   // y_{hi,lo}
+            const unsigned long long h = tame_mix64(tame_mix64(key ^ 0x9e3779b97f4a7c15ull) ^ tame_mix64(a) ^ (tame_mix64(b) * 3ull));
+            sum += (i < j) ? h : (0ull - h);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (threadIdx.x == 0) atomicAdd(acc, sum);
+}
+
 // red6 = {sq, quad, lp0, lpt, ent, tr}: deterministic two-level sum of the per-block partials
 __global__ void __launch_bounds__(256) k_reduce6(const double* part_ll, int nb_ll, const double* part_cell, int nb_cell,
                                                  double* red6) {
@@ -457,6 +486,20 @@ int tame_bind_Y(tame_handle* h, const double* Y) {
         CK(cudaMemcpyAsync(&bad, h->sym_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         h->y_symmetric = (bad == 0);
+    }
+    if (h->P.world > 1 && h->comm && !(sv && atoi(sv) == 0)) {
+        // multi-GPU: signed hash sum over every rank's rows (needs tame_comm_init before tame_bind_Y)
+        unsigned long long* acc = nullptr;
+        CK(cudaMalloc((void**)&acc, sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(acc, 0, sizeof(unsigned long long), h->stream));
+        k_symhash<<<grid, block, 0, h->stream>>>(h->P, acc);
+        tame_count_launch(1);
+        NK(g_nccl.AllReduce(acc, acc, 1, ncclUint64, ncclSum, h->comm, h->stream));
+        unsigned long long total = 1;
+        CK(cudaMemcpyAsync(&total, acc, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(acc);
+        h->y_symmetric = (total == 0ull);
     }
     h->y_bound = true;
     return TAME_OK;

@@ -27,6 +27,8 @@ dist.init_process_group("nccl", device_id=dev)
 lib = _lib.load()
 n, T, r, lr, iters = 256, 9, 3, 0.3, 2
 c, Y, Xm, Xc = _random_problem(n, T, r, seed=77)
+if os.environ.get("TAME_TEST_ASYM") == "1":
+    Y = Y.copy(); Y[3, 200, 2, 0] += 0.125          # one dyad no longer mirror-consistent -> full ELBO pass on every rank
 for meth in ("good", "naive"):
     mode = orc.MODE_OF[meth]
     cfg, keep = make_config(c, lr, mode, device=rank, world=world, rank=rank, panel=64)
@@ -61,7 +63,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("scheduler", ["fused", "panel"])
+@pytest.mark.parametrize("scheduler", ["fused", "panel", "fused-asymmetricY"])
 def test_two_rank_fit_matches_oracle(tmp_path, scheduler):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -69,10 +71,12 @@ def test_two_rank_fit_matches_oracle(tmp_path, scheduler):
     script.write_text(f"ROOT = {ROOT!r}\n" + WORKER)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     env = dict(os.environ)
+    env.pop("TAME_SWEEP", None)
+    env.pop("TAME_TEST_ASYM", None)
     if scheduler == "panel":
         env["TAME_SWEEP"] = "panel"
-    else:
-        env.pop("TAME_SWEEP", None)
+    if scheduler == "fused-asymmetricY":
+        env["TAME_TEST_ASYM"] = "1"
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", str(port), str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
