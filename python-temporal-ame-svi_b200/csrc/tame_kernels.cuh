@@ -1198,6 +1198,189 @@ __global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* part
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_llmse_mma: the same pass with the bilinear terms on the FP64 tensor cores (mma.sync.m8n8k4.f64 = DMMA).
+//   For a fixed time step the 8x8 blocks  d0[i][j] = U_i.V_j  and  d1[i][j] = V_i.U_j  of an (8 rows x 8 partners) tile
+//   are R/4 DMMA each: A = the tile's own rows (kept in registers for the whole pass), B = the partners' records staged
+//   in shared memory.  The accumulator fragment gives every lane two dyads (row g, partners 2q, 2q+1), whose Y entries
+//   it reads from the cp.async ring (padded pitches 517/257 so that a quarter-warp's 16-byte reads hit distinct banks).
+//   CTA = 8 warps = 16 rows x 32 time steps; warp w owns time steps t0+4w..+3 and both 8-row tiles.  ~0.36 issued
+//   instructions per dyad instead of ~1.25.  R must be a multiple of 4.
+// grid (ceil(T/32), ceil(nloc/16)), block 256; partial (grid.y*grid.x, 2).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tame_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int R>
+struct TameMma {
+    static constexpr int D = 2 + 2 * R, JC = 8, RS = TameRec<D>::RS, PIECES = D / 2, KS = R / 4;
+    static constexpr int PR = 257, PJ = 517;                       // ring pitches in 16-byte units (see header)
+    static constexpr int MJ = 32 * RS + 4;                         // partner pitch of the staged records (doubles)
+    static constexpr size_t Y_BYTES = (size_t)2 * JC * PJ * sizeof(double2);
+    static constexpr size_t M_BYTES = (size_t)2 * JC * MJ * sizeof(double);
+    static constexpr size_t SMEM = Y_BYTES + M_BYTES;
+};
+
+template <int R, bool SYM>
+__global__ void __launch_bounds__(256, 1) k_llmse_mma(TameParams P, double* partial) {
+    using TM = TameMma<R>;
+    constexpr int D = TM::D, JC = TM::JC, RS = TM::RS, KS = TM::KS, PR = TM::PR, PJ = TM::PJ, MJ = TM::MJ, RT = 16;
+    static_assert(R % 4 == 0, "DMMA k-step is 4");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* Yr = reinterpret_cast<double2*>(smem_raw);                          // [2][JC*PJ]
+    double* Mb = reinterpret_cast<double*>(smem_raw + TM::Y_BYTES);              // [2][JC*MJ]
+    __shared__ double red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int t0 = blockIdx.x * 32;
+    const int lrow0 = blockIdx.y * RT;
+    const int gfirst = tame_grow(min(lrow0, P.nloc - 1), P.panel, P.world, P.rank);   // first node of the tile (16 | panel)
+
+    // ---- copy role: this thread moves the dyads of rows lrow0 + 2*warp + {0,1} at time t0 + lane
+    const double* yrow[2];
+    bool rvc[2];
+    int gic[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        int l = lrow0 + 2 * warp + rr;
+        rvc[rr] = (l < P.nloc) && (t0 + lane < P.T);
+        l = min(l, P.nloc - 1);
+        gic[rr] = tame_grow(l, P.panel, P.world, P.rank);
+        yrow[rr] = P.Y + ((size_t)l * P.n * P.T + min(t0 + lane, P.T - 1)) * 2;
+    }
+    const size_t jstride = (size_t)P.T * 2;
+    auto issue_chunk = [&](int buf, int jc) {
+        double2* yb = Yr + (size_t)buf * JC * PJ;
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) {
+            const int j = jc + jj;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const bool ok = rvc[rr] && (j < P.n) && (SYM ? (j > gic[rr]) : (j != gic[rr]));
+                tame_cp_async16(yb + jj * PJ + rr * PR + tid, yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
+            }
+        }
+        double* mb = Mb + (size_t)buf * JC * MJ;
+        for (int e = tid; e < JC * 32 * TM::PIECES; e += 256) {
+            const int piece = e % TM::PIECES, tl = (e / TM::PIECES) & 31, jj = e / (TM::PIECES * 32);
+            const int j = jc + jj, tt = t0 + tl;
+            const bool ok = (j < P.n) && (tt < P.T);
+            const double* src = P.Xm + ((size_t)min(j, P.n - 1) * P.T + min(tt, P.T - 1)) * D + piece * 2;
+            tame_cp_async16(mb + jj * MJ + tl * RS + piece * 2, src, ok);
+        }
+        tame_cp_async_commit();
+    };
+
+    // ---- tensor-core role: time steps t0 + 4*warp + tt, row tiles 0/1 (rows lrow0 + 8*tile + g)
+    double aU[4][2][KS], aV[4][2][KS], oa[4][2], ob[4][2];
+    int grow[2];
+    bool rowok[2];
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+        int l = lrow0 + 8 * tile + g;
+        rowok[tile] = l < P.nloc;
+        l = min(l, P.nloc - 1);
+        grow[tile] = tame_grow(l, P.panel, P.world, P.rank);
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+            const int t = min(t0 + 4 * warp + tt, P.T - 1);
+            const double* m = P.Xm + ((size_t)grow[tile] * P.T + t) * D;
+            oa[tt][tile] = m[0];
+            ob[tt][tile] = m[1];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                aU[tt][tile][ks] = m[2 + 4 * ks + q];          // A[row g][k q] = U_i[k]
+                aV[tt][tile][ks] = m[2 + R + 4 * ks + q];      // A[row g][k q] = V_i[k]
+            }
+        }
+    }
+    double S00 = 0.0, S01 = 0.0, S11 = 0.0, SL = 0.0;
+
+    const int jbeg = SYM ? (gfirst / JC) * JC : 0;
+    const int nchunks = (P.n - jbeg + JC - 1) / JC;
+    issue_chunk(0, jbeg);
+    if (nchunks > 1) issue_chunk(1, jbeg + JC);
+    for (int c = 0; c < nchunks; ++c) {
+        const int jc = jbeg + c * JC, buf = c & 1;
+        if (c + 1 < nchunks) tame_cp_async_wait<1>(); else tame_cp_async_wait<0>();
+        __syncthreads();                                       // chunk c (Y dyads + partner records) is visible to the CTA
+        const double2* yb = Yr + (size_t)buf * JC * PJ;
+        const double* mb = Mb + (size_t)buf * JC * MJ;
+        // 0: all partners below the tile's rows, 1: all above (and inside the matrix), 2: mixed / tail
+        const int kind = (jc + JC <= gfirst) ? 0 : ((jc > gfirst + RT - 1 && jc + JC <= P.n) ? 1 : 2);
+        const int j0 = jc + 2 * q, j1 = j0 + 1;               // this lane's two partners
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+            const int tl = 4 * warp + tt;
+            const bool tok = (t0 + tl) < P.T;
+            // B fragments: B[k q][partner g]
+            double bV[KS], bU[KS];
+            const double* recg = mb + g * MJ + tl * RS;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                bU[ks] = recg[2 + 4 * ks + q];
+                bV[ks] = recg[2 + R + 4 * ks + q];
+            }
+            const double2 ab0 = *reinterpret_cast<const double2*>(mb + (2 * q) * MJ + tl * RS);        // (a_j, b_j) of partner j0
+            const double2 ab1 = *reinterpret_cast<const double2*>(mb + (2 * q + 1) * MJ + tl * RS);    // partner j1
+#pragma unroll
+            for (int tile = 0; tile < 2; ++tile) {
+                double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;      // d0/d1 for partners j0, j1
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    tame_dmma(d00, d01, aU[tt][tile][ks], bV[ks]);      // U_i . V_j
+                    tame_dmma(d10, d11, aV[tt][tile][ks], bU[ks]);      // V_i . U_j
+                }
+                // the two dyads of this lane: row (8*tile + g) -> copied by warp (4*tile + g/2), rr = g & 1
+                const int slot = (g & 1) * PR + (4 * tile + (g >> 1)) * 32 + tl;
+                const double2 y0 = yb[(2 * q) * PJ + slot];
+                const double2 y1 = yb[(2 * q + 1) * PJ + slot];
+                const int gi = grow[tile];
+                const double e00 = y0.x - ((oa[tt][tile] + ab0.y) + d00), e01 = y0.y - ((ab0.x + ob[tt][tile]) + d10);
+                const double e10 = y1.x - ((oa[tt][tile] + ab1.y) + d01), e11 = y1.y - ((ab1.x + ob[tt][tile]) + d11);
+                const bool base = rowok[tile] && tok;
+                if (kind == 1) {
+                    if (base) {
+                        S00 = fma(e00, e00, S00); S01 = fma(e00, e01, S01); S11 = fma(e01, e01, S11);
+                        S00 = fma(e10, e10, S00); S01 = fma(e10, e11, S01); S11 = fma(e11, e11, S11);
+                    }
+                } else if (kind == 0) {
+                    if (base && !SYM) { SL = fma(e00, e00, SL); SL = fma(e01, e01, SL); SL = fma(e10, e10, SL); SL = fma(e11, e11, SL); }
+                } else {
+                    if (base && j0 < P.n && j0 != gi) {
+                        if (j0 > gi) { S00 = fma(e00, e00, S00); S01 = fma(e00, e01, S01); S11 = fma(e01, e01, S11); }
+                        else if (!SYM) { SL = fma(e00, e00, SL); SL = fma(e01, e01, SL); }
+                    }
+                    if (base && j1 < P.n && j1 != gi) {
+                        if (j1 > gi) { S00 = fma(e10, e10, S00); S01 = fma(e10, e11, S01); S11 = fma(e11, e11, S11); }
+                        else if (!SYM) { SL = fma(e10, e10, SL); SL = fma(e11, e11, SL); }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                       // every warp is done with buffer `buf`
+        if (c + 2 < nchunks) issue_chunk(buf, jc + 2 * JC);
+    }
+    double sq = SYM ? 2.0 * (S00 + S11) : (S00 + S11) + SL;
+    double quad = P.p0 * S00 + 2.0 * P.q * S01 + P.p1 * S11;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    }
+    if (lane == 0) { red[0][warp] = sq; red[1][warp] = quad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0, qd = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { s += red[0][w]; qd += red[1][w]; }
+        size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        partial[b * 2 + 0] = s;
+        partial[b * 2 + 1] = qd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_cellterms: per (i,t) block terms of the ELBO, one warp per owned cell.
 //   ent   = 0.5 (d (1+log 2pi) + logdet X_cov[i,t])                                    structured_mf.py:202-209
 //   t==0 : lp0 = -0.5 (logdet S0 + mu' S0inv mu + tr(S0inv X_cov) + d log 2pi)         :152-173

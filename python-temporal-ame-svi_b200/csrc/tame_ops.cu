@@ -1,5 +1,8 @@
 // tame_ops.cu -- instantiates the kernels of tame_kernels.cuh for one latent dimension (-DTAME_R=r) and
 // exports their launchers through a function table; tame_api.cu picks the table by cfg.r.
+#include <cstdlib>
+#include <cstring>
+
 #include "tame_kernels.cuh"
 
 #ifndef TAME_R
@@ -81,9 +84,45 @@ int chain_max_T() {
 }
 
 constexpr int LL_RW = 2, LL_NW = 16;      // k_llmse tile: 16 warps x 2 rows
-int llmse_blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 31) / 32); }
+int llmse_blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 15) / 16); }   // upper bound over both variants
+
+template <int RR, bool OK = (RR % 4 == 0)>
+struct LlmseMma {
+    static bool launch(const TameParams&, double*, int*, int, cudaStream_t) { return false; }
+    static int blocks(const TameParams&) { return 0; }
+};
+template <int RR>
+struct LlmseMma<RR, true> {
+    static int blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 15) / 16); }
+    static bool launch(const TameParams& P, double* partial, int* nblocks, int symmetric, cudaStream_t st) {
+        dim3 grid((P.T + 31) / 32, (P.nloc + 15) / 16);
+        constexpr size_t smem = TameMma<RR>::SMEM;
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_llmse_mma<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_llmse_mma<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = true;
+        }
+        if (symmetric) k_llmse_mma<RR, true><<<grid, 256, smem, st>>>(P, partial);
+        else k_llmse_mma<RR, false><<<grid, 256, smem, st>>>(P, partial);
+        *nblocks = grid.x * grid.y;
+        tame_count_launch(1);
+        return true;
+    }
+};
+// default: DMMA tile where it wins (r = 4: -23 % on config 3), DFMA ring for r = 8 (the DMMA tile's chunk-granular double
+// buffer keeps half as many bytes in flight and re-reads the partner records per 16 rows: +10 % at config 4).
+// TAME_LLMSE=mma|dfma overrides (read per call so that tests can cover both).
+bool llmse_use_mma() {
+    if (R % 4 != 0) return false;
+    const char* v = getenv("TAME_LLMSE");
+    if (v && strcmp(v, "dfma") == 0) return false;
+    if (v && strcmp(v, "mma") == 0) return true;
+    return R == 4;
+}
 
 void launch_llmse(const TameParams& P, double* partial, int* nblocks, int symmetric, cudaStream_t st) {
+    if (llmse_use_mma() && LlmseMma<R>::launch(P, partial, nblocks, symmetric, st)) return;
     dim3 grid((P.T + 31) / 32, (P.nloc + 31) / 32);
     constexpr size_t smem = TameStream<R, RW>::SMEM;      // ring PD x LL_RW x 512 x 16 B == PD x RW x 256 x 16 B
     static_assert(LL_RW * LL_NW == RW * 8, "same ring footprint");

@@ -270,3 +270,25 @@ def test_fit_batch_matches_per_fit_oracle():
         assert _trace_ok(el[f, :nd[f]], oel) and _trace_ok(ms[f, :nd[f]], oms)
         assert rel_err(dev[f][1].cpu().numpy(), Om) < TOL and rel_err(dev[f][2].cpu().numpy(), Oc) < TOL
     assert stopped_early > 0, "the test should exercise the per-fit early stop"
+
+
+@pytest.mark.parametrize("variant", ["mma", "dfma"])
+@pytest.mark.parametrize("shape", [(96, 33, 4), (129, 6, 8), (200, 40, 8)])
+def test_elbo_pass_variants_agree_with_oracle(shape, variant, monkeypatch):
+    """Both implementations of the fused ELBO/MSE pass -- FP64 tensor-core (DMMA) tiles and the DFMA ring -- on mirror-
+    consistent Y (triangular pass) and on a perturbed Y (full pass)."""
+    from gpu_util import DeviceFit
+    monkeypatch.setenv("TAME_LLMSE", variant)
+    n, T, r = shape
+    c, Y, Xm, Xc = _random_problem(n, T, r, seed=4242 + n)
+    for asym in (False, True):
+        Yt = Y.copy()
+        if asym:
+            Yt[5, 60, 1, 1] -= 0.25
+        f = DeviceFit(Yt, Xm, Xc, c, 0.3, orc.GOOD)
+        got = f.elbo_mse()
+        f.close()
+        ref = list(orc.elbo_parts(Yt, Xm, Xc, c, orc.GOOD))
+        assert abs(got[1] - ref[0]) <= TOL * abs(ref[0]), (variant, asym, got[1], ref[0])
+        mse = orc.reconstruction_mse(Yt, Xm, c)
+        assert abs(got[5] - mse) <= TOL * abs(mse)
