@@ -1094,11 +1094,17 @@ __global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* part
 #pragma unroll
     for (int rr = 0; rr < RW; ++rr) S00[rr] = S01[rr] = S11[rr] = SL[rr] = 0.0;
     const int gfirst = tame_grow(min(blockIdx.y * RT, P.nloc - 1), P.panel, P.world, P.rank);   // first node of the tile
+    // partner range of this CTA: SYM skips the partners below the tile; gridDim.z splits the range when the grid would not
+    // fill the GPU otherwise (few rows per rank on many GPUs)
+    const int jlo = SYM ? (gfirst / JC) * JC : 0;
+    const int zlen = (((P.n - jlo + (int)gridDim.z - 1) / (int)gridDim.z + JC - 1) / JC) * JC;
+    const int jbeg = jlo + (int)blockIdx.z * zlen, jend = min(P.n, jbeg + zlen);
+    const int nchunks = (jend > jbeg) ? (jend - jbeg + JC - 1) / JC : 0;
 
     auto issue_y = [&](int j, int slot) {
 #pragma unroll
         for (int rr = 0; rr < RW; ++rr) {
-            const bool ok = rv[rr] && (j < P.n) && (SYM ? (j > gi[rr]) : (j != gi[rr]));
+            const bool ok = rv[rr] && (j < jend) && (SYM ? (j > gi[rr]) : (j != gi[rr]));
             tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
         }
     };
@@ -1106,14 +1112,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* part
         for (int e = tid; e < JC * 32 * TS::PIECES; e += NT) {
             const int piece = e % TS::PIECES, tl = (e / TS::PIECES) & 31, jj = e / (TS::PIECES * 32);
             const int j = jc + jj, tt = t0 + tl;
-            const bool ok = (j < P.n) && (tt < P.T);
+            const bool ok = (j < jend) && (tt < P.T);
             const double* src = P.Xm + ((size_t)min(j, P.n - 1) * P.T + min(tt, P.T - 1)) * D + piece * 2;
             tame_cp_async16(&Mb[buf][jj][tl][piece * 2], src, ok);
         }
     };
-    const int jbeg = SYM ? (gfirst / JC) * JC : 0;                  // SYM: partners below the tile are never needed
-    const int nchunks = (P.n - jbeg + JC - 1) / JC;
-    issue_m(0, jbeg);
+    if (nchunks > 0) issue_m(0, jbeg);
 #pragma unroll
     for (int s = 0; s < PD; ++s) {
         issue_y(jbeg + s, s);
@@ -1122,7 +1126,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* part
     for (int c = 0; c < nchunks; ++c) {
         const int jc = jbeg + c * JC, buf = c & 1;
         // chunk-uniform case: 0 all partners below the tile's rows, 1 all above, 2 touches the tile's own nodes / the tail
-        const int kind = (jc + JC <= gfirst) ? 0 : ((jc > gfirst + RT - 1 && jc + JC <= P.n) ? 1 : 2);
+        const int kind = (jc + JC <= gfirst) ? 0 : ((jc > gfirst + RT - 1 && jc + JC <= jend) ? 1 : 2);
 #pragma unroll
         for (int jj = 0; jj < JC; ++jj) {
             const int j = jc + jj;
@@ -1156,7 +1160,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* part
                 } else if (kind == 0) {
                     SL[rr] = fma(e0, e0, SL[rr]);
                     SL[rr] = fma(e1, e1, SL[rr]);
-                } else if (j < P.n && j != gi[rr]) {
+                } else if (j < jend && j != gi[rr]) {
                     if (j > gi[rr]) {
                         S00[rr] = fma(e0, e0, S00[rr]);
                         S01[rr] = fma(e0, e1, S01[rr]);
@@ -1191,7 +1195,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* part
         double s = 0.0, qd = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) { s += red[0][w]; qd += red[1][w]; }
-        size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        size_t b = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         partial[b * 2 + 0] = s;
         partial[b * 2 + 1] = qd;
     }

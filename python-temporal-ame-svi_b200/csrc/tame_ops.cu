@@ -1,5 +1,6 @@
 // tame_ops.cu -- instantiates the kernels of tame_kernels.cuh for one latent dimension (-DTAME_R=r) and
 // exports their launchers through a function table; tame_api.cu picks the table by cfg.r.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -84,7 +85,7 @@ int chain_max_T() {
 }
 
 constexpr int LL_RW = 2, LL_NW = 16;      // k_llmse tile: 16 warps x 2 rows
-int llmse_blocks(const TameParams& P) { return ((P.T + 31) / 32) * ((P.nloc + 15) / 16); }   // upper bound over both variants
+int llmse_blocks(const TameParams& P) { return 4 * ((P.T + 31) / 32) * ((P.nloc + 15) / 16); }   // upper bound over both variants (x4: grid.z split)
 
 template <int RR, bool OK = (RR % 4 == 0)>
 struct LlmseMma {
@@ -132,9 +133,14 @@ void launch_llmse(const TameParams& P, double* partial, int* nblocks, int symmet
         cudaFuncSetAttribute(k_llmse<R, LL_RW, LL_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
+    // split the partner range over grid.z when the (row tile x time slice) grid alone would leave SMs idle
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int base = grid.x * grid.y;
+    grid.z = (base >= 3 * sms) ? 1 : std::min(4, (3 * sms + base - 1) / base);
     if (symmetric) k_llmse<R, LL_RW, LL_NW, true><<<grid, LL_NW * 32, smem, st>>>(P, partial);
     else k_llmse<R, LL_RW, LL_NW, false><<<grid, LL_NW * 32, smem, st>>>(P, partial);
-    *nblocks = grid.x * grid.y;
+    *nblocks = grid.x * grid.y * grid.z;
     tame_count_launch(1);
 }
 
