@@ -288,6 +288,14 @@ def elbo_parts(Y, Xm, Xc, c, mode):
             tr = np.trace(Xc[:, t], axis1=1, axis2=2)
             corr = 0.1 * (tr[iu[0]] + tr[iu[1]]) * tr_Rinv / d        # structured_mf.py:142-144
         ll += np.sum(-0.5 * (c["logdet_R"] + quad + corr + 2 * LOG_2PI))
+    lp0, lpt, ent = elbo_state_parts(Xm, Xc, c)
+    return float(ll), lp0, lpt, ent
+
+
+def elbo_state_parts(Xm, Xc, c):
+    """(LP0, LPT, H): the ELBO terms that only read the variational state -- structured_mf.py:148-209 /
+    naive_mf.py:134-191.  O(n T d^3), so it also serves at sizes where Y does not fit on the host."""
+    T, d = c["T"], c["d"]
     quad0 = np.einsum("ia,ab,ib->i", Xm[:, 0], c["S0_inv"], Xm[:, 0])
     tr0 = np.einsum("ab,iba->i", c["S0_inv"], Xc[:, 0])
     lp0 = np.sum(-0.5 * (c["logdet_S0"] + quad0 + tr0 + d * LOG_2PI))
@@ -299,7 +307,7 @@ def elbo_parts(Y, Xm, Xc, c, mode):
         lpt = np.sum(-0.5 * (c["logdet_Q"] + quadt + trt + d * LOG_2PI))
     logdet = np.linalg.slogdet(Xc)[1]
     ent = np.sum(0.5 * (d * (1 + LOG_2PI) + logdet))
-    return float(ll), float(lp0), float(lpt), float(ent)
+    return float(lp0), float(lpt), float(ent)
 
 
 def elbo(Y, Xm, Xc, c, mode):

@@ -1,0 +1,158 @@
+"""Parity at the sizes BASELINE.json quotes (configs 3 and 4), where the oracle cannot run a whole sweep.
+
+Size-independent checks of the SAME quantities the small-shape parity tests compare in full:
+
+* spot nodes -- a Gauss-Seidel sweep is the composition of its node updates, so node i of the device result must equal
+  the oracle's `update_node` (structured_mf.py:220-287 / naive_mf.py:207-282) applied to the state "new means for
+  j < i, old means for j >= i" with row i of Y.  O(n T d^2) per node on the host; nodes are picked at the 32/64-node
+  structure boundaries of the CUDA schedule (sub-block, refresh, panel) and at random, in the SECOND sweep so that the
+  epoch handling of the persistent kernel is covered too.
+* ELBO / MSE -- LP0, LPT, H from the oracle on the full state; LL and the reconstruction MSE from a plain torch FP64
+  restatement of static_ame.py:189-238 + structured_mf.py:124-146 evaluated on the device in row chunks (Y at config 4
+  is 137 GB and never leaves HBM).
+* the ELBO-pass variants (DFMA ring / DMMA tile) agree on the full-size input.
+
+Tolerance: rel 1e-9 (north_star), written where it is used.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tame_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+# (n, T, r, method, lr): config 3, two mid sizes that exercise ragged T / odd r / the column-part split (n >= 2048),
+# and config 4 itself.
+SCALE = [
+    (1024, 64, 4, "good", 0.3),
+    (2048, 40, 8, "bad", 0.05),
+    (2304, 33, 3, "naive", 0.3),
+    (8192, 128, 8, "good", 0.3),
+]
+
+
+class _OneRow:
+    """X_cov stand-in holding only node i's blocks, indexable as [i, t] like the oracle expects."""
+
+    def __init__(self, i, rows):
+        self.i, self.rows = i, rows
+
+    def __getitem__(self, k):
+        assert k[0] == self.i
+        return self.rows[k[1]]
+
+    def __setitem__(self, k, v):
+        assert k[0] == self.i
+        self.rows[k[1]] = v
+
+
+def _device_problem(n, T, r, seed, dev):
+    """Mirror-consistent Y generated in HBM (tame_generate_Y), a random start state on the device."""
+    from tame_b200 import _lib
+    lib = _lib.load()
+    c = orc.model_constants(n, T, r)
+    d = c["d"]
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Xt = torch.zeros(n, T, d, dtype=torch.float64)
+    Xt[:, 0] = torch.randn(n, d, generator=g, dtype=torch.float64) * 0.6
+    for t in range(1, T):
+        Xt[:, t] = 0.8 * Xt[:, t - 1] + 0.3 * torch.randn(n, d, generator=g, dtype=torch.float64)
+    Xt_d = Xt.to(dev)
+    Y = torch.empty(n, n, T, 2, dtype=torch.float64, device=dev)
+    R = np.ascontiguousarray(c["R"].reshape(4))
+    _lib.check(lib.tame_generate_Y(n, T, r, _lib.dptr(R), Xt_d.data_ptr(), C.c_uint64(seed), 0, n, Y.data_ptr(),
+                                   torch.cuda.current_stream(dev).cuda_stream))
+    gd = torch.Generator(device=dev).manual_seed(seed + 1)
+    Xm = 0.1 * torch.randn(n, T, d, generator=gd, dtype=torch.float64, device=dev)
+    B = 0.1 * torch.randn(n, T, d, 2, generator=gd, dtype=torch.float64, device=dev)
+    Xc = 0.5 * torch.eye(d, dtype=torch.float64, device=dev) + B @ B.transpose(-1, -2)
+    torch.cuda.synchronize(dev)
+    return c, Y, Xm.contiguous(), Xc.contiguous()
+
+
+def _torch_ll_mse(Y, Xm, Xc, c, mode, chunk=64):
+    """LL (i<j dyads, structured_mf.py:124-146 / naive_mf.py:114-132) and the MSE numerator (temporal_ame.py:255-291)
+    as plain torch FP64 on the device, row chunk by row chunk."""
+    n, T, r, d = c["n"], c["T"], c["r"], c["d"]
+    p0, q, p1 = float(c["R_inv"][0, 0]), float(c["R_inv"][0, 1]), float(c["R_inv"][1, 1])
+    a, b = Xm[:, :, 0], Xm[:, :, 1]
+    U, V = Xm[:, :, 2:2 + r], Xm[:, :, 2 + r:]
+    tr = torch.diagonal(Xc, dim1=-2, dim2=-1).sum(-1)                    # (n, T)
+    k = 0.0 if mode == orc.NAIVE else 0.1 * (p0 + p1) / d
+    const = float(c["logdet_R"]) + 2 * orc.LOG_2PI
+    cols = torch.arange(n, device=Y.device)
+    ll = torch.zeros((), dtype=torch.float64, device=Y.device)
+    se = torch.zeros((), dtype=torch.float64, device=Y.device)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        rows = torch.arange(lo, hi, device=Y.device)
+        e0 = Y[lo:hi, :, :, 0] - (a[lo:hi, None, :] + b[None, :, :] + torch.einsum("itk,jtk->ijt", U[lo:hi], V))
+        e1 = Y[lo:hi, :, :, 1] - (a[None, :, :] + b[lo:hi, None, :] + torch.einsum("jtk,itk->ijt", U, V[lo:hi]))
+        upper = (cols[None, :] > rows[:, None])[:, :, None]
+        offd = (cols[None, :] != rows[:, None])[:, :, None]
+        quad = p0 * e0 * e0 + 2 * q * e0 * e1 + p1 * e1 * e1
+        corr = k * (tr[lo:hi, None, :] + tr[None, :, :])
+        ll += torch.sum(torch.where(upper, -0.5 * (const + quad + corr), 0.0))
+        se += torch.sum(torch.where(offd, e0 * e0 + e1 * e1, 0.0))
+        del e0, e1, quad, corr
+    return float(ll), float(se) / (n * (n - 1) * T)
+
+
+@pytest.mark.parametrize("n,T,r,meth,lr", SCALE)
+def test_full_size_spot_nodes_and_elbo(n, T, r, meth, lr, monkeypatch):
+    from gpu_util import DeviceFit
+    dev = torch.device("cuda", 0)
+    d = 2 + 2 * r
+    need = (n * n * T * 2 + 2 * n * T * d * d) * 8 + 12 * n * T * 64 * 8 + (2 << 30)
+    torch.cuda.empty_cache()
+    if torch.cuda.mem_get_info(dev)[0] < need:
+        pytest.skip("not enough free HBM for this shape")
+    mode = orc.MODE_OF[meth]
+    c, Y, Xm, Xc = _device_problem(n, T, r, seed=4000 + n + r, dev=dev)
+    f = DeviceFit(Y, Xm, Xc, c, lr, mode)
+    try:
+        f.sweep()
+        torch.cuda.synchronize()
+        rng = np.random.default_rng(n + T)
+        spots = sorted({0, 1, 31, 32, 33, 63, 64, 65, n // 2 - 1, n // 2, n - 65, n - 33, n - 32, n - 1,
+                        *rng.integers(0, n, 4).tolist()})
+        old_m = f.Xm.cpu().numpy()
+        old_c = {i: f.Xc[i].cpu().numpy() for i in spots}
+        f.sweep()
+        el = f.elbo_mse()
+        new_m = f.Xm.cpu().numpy()
+        assert np.all(np.isfinite(new_m)) and np.all(np.isfinite(el))
+        worst_m = worst_c = 0.0
+        mix = new_m.copy()
+        for i in spots:
+            mix[:i] = new_m[:i]
+            mix[i:] = old_m[i:]
+            row = f.Y[i].cpu().numpy()[None]
+            cov = _OneRow(i, old_c[i].copy())
+            orc.update_node(row, mix, cov, i, c, lr, mode, row=0)
+            got_c = f.Xc[i].cpu().numpy()
+            em = np.max(np.abs(mix[i] - new_m[i])) / np.max(np.abs(mix[i]))
+            ec = np.max(np.abs(cov.rows - got_c)) / np.max(np.abs(cov.rows))
+            worst_m, worst_c = max(worst_m, em), max(worst_c, ec)
+            assert em < TOL, (i, em)          # rel 1e-9 on the node's means
+            assert ec < TOL, (i, ec)          # rel 1e-9 on the node's covariance blocks
+        # ELBO parts and MSE of the state after the second sweep
+        lp0, lpt, ent = orc.elbo_state_parts(new_m, f.Xc.cpu().numpy(), c)
+        ll, mse = _torch_ll_mse(f.Y, f.Xm, f.Xc, c, mode)
+        ref = np.array([ll + lp0 + lpt + ent, ll, lp0, lpt, ent, mse])
+        assert np.all(np.abs(el - ref) <= TOL * np.abs(ref)), (el, ref)
+        # the other ELBO-pass variant on the same state
+        default_is_mma = (r == 4)
+        monkeypatch.setenv("TAME_LLMSE", "dfma" if default_is_mma else "mma")
+        el2 = f.elbo_mse()
+        assert np.all(np.abs(el2 - el) <= 1e-11 * np.abs(el)), (el, el2)
+        print(f"scale n={n} T={T} r={r} {meth}: spot nodes {len(spots)} worst mean {worst_m:.2e} cov {worst_c:.2e}; "
+              f"ELBO dev {el[0]:.15e} ref {ref[0]:.15e}")
+    finally:
+        f.close()
+        del f, Y, Xm, Xc
+        torch.cuda.empty_cache()
