@@ -553,7 +553,10 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     double* cstPQ = cstQP + D * D;                                // Phi'Qinv  (D*D)
     S* warps = reinterpret_cast<S*>(cstPQ + D * D);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 2 * D * D; e += blockDim.x) cstQP[e] = P.cst[3 * D * D + e];
+    for (int e = threadIdx.x; e < 2 * D * D; e += blockDim.x) {      // stored transposed: [k][row], conflict-free per k
+        const int m = e / (D * D), rc = e % (D * D);
+        cstQP[m * D * D + (rc % D) * D + rc / D] = P.cst[3 * D * D + e];
+    }
     if (threadIdx.x < TAME_CHAIN_WPC) { warps[threadIdx.x].h_ready = i0 - 1; warps[threadIdx.x].c_done = i0 - 1; }
     __syncthreads();
     // a chain CTA carries 8 warps: warps 0..3 are the chain warps of 4 consecutive time steps (one per SM sub-partition),
@@ -823,22 +826,22 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             if (has_prev) {
 #pragma unroll
                 for (int k = 0; k + 2 < D; k += 3) {
-                    p0 = fma(cstQP[cc * D + k], sm.mprev[k], p0);
-                    p1 = fma(cstQP[cc * D + k + 1], sm.mprev[k + 1], p1);
-                    p2 = fma(cstQP[cc * D + k + 2], sm.mprev[k + 2], p2);
+                    p0 = fma(cstQP[k * D + cc], sm.mprev[k], p0);
+                    p1 = fma(cstQP[(k + 1) * D + cc], sm.mprev[k + 1], p1);
+                    p2 = fma(cstQP[(k + 2) * D + cc], sm.mprev[k + 2], p2);
                 }
 #pragma unroll
-                for (int k = (D / 3) * 3; k < D; ++k) p0 = fma(cstQP[cc * D + k], sm.mprev[k], p0);
+                for (int k = (D / 3) * 3; k < D; ++k) p0 = fma(cstQP[k * D + cc], sm.mprev[k], p0);
             }
             if (has_next) {
 #pragma unroll
                 for (int k = 0; k + 2 < D; k += 3) {
-                    n0 = fma(cstPQ[cc * D + k], sm.mnext[k], n0);
-                    n1 = fma(cstPQ[cc * D + k + 1], sm.mnext[k + 1], n1);
-                    n2 = fma(cstPQ[cc * D + k + 2], sm.mnext[k + 2], n2);
+                    n0 = fma(cstPQ[k * D + cc], sm.mnext[k], n0);
+                    n1 = fma(cstPQ[(k + 1) * D + cc], sm.mnext[k + 1], n1);
+                    n2 = fma(cstPQ[(k + 2) * D + cc], sm.mnext[k + 2], n2);
                 }
 #pragma unroll
-                for (int k = (D / 3) * 3; k < D; ++k) n0 = fma(cstPQ[cc * D + k], sm.mnext[k], n0);
+                for (int k = (D / 3) * 3; k < D; ++k) n0 = fma(cstPQ[k * D + cc], sm.mnext[k], n0);
             }
             hval = hb + ((c >= 2 && c < D) ? sm.hin[c - 2] : 0.0);
             hval += (p0 + p1) + p2;          // Qinv Phi mu_{t-1}      (structured_mf.py:258)
@@ -885,10 +888,10 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
             if (P.mode == 0) {
                 const double dinv = 1.0 / (pdiag + 1e-8);
 #pragma unroll
-                for (int k = 0; k < D; ++k) sm.Cf[c * D + k] = (k == c) ? dinv : 0.0;
+                for (int k = 0; k < D; ++k) sm.Cf[k * D + c] = (k == c) ? dinv : 0.0;
             } else {
 #pragma unroll
-                for (int k = 0; k < D; ++k) sm.Cf[c * D + k] = crow[k];
+                for (int k = 0; k < D; ++k) sm.Cf[k * D + c] = crow[k];     // exactly symmetric: [k][c] is conflict-free
             }
         }
         __syncwarp();
@@ -1399,7 +1402,13 @@ __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0
     __shared__ double rowb[8][TAME_GJ_ROWB(D)];
     __shared__ double vec[8][2 * D];
     __shared__ double red[8][4];
+    __shared__ double cT[3][D * D];      // S0inv, Qinv, Phi transposed: cT[m][k * D + c] = M[c][k]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < 3 * D * D; e += blockDim.x) {
+        const int m = e / (D * D), rc = e % (D * D);
+        cT[m][(rc % D) * D + rc / D] = P.cst[(m == 2 ? 5 : m) * D * D + rc];
+    }
+    __syncthreads();
     const double LOG2PI = 1.8378770664093454835606594728112;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const long ncell = (long)P.nloc * P.T;
@@ -1419,22 +1428,22 @@ __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0
             vec[warp][D + c] = (t > 0) ? P.Xm[((size_t)i * P.T + t - 1) * D + c] : 0.0;
         }
         __syncwarp();
-        const double* A = P.cst + (t == 0 ? 0 : 1) * D * D;   // S0inv or Qinv
-        const double* Phi = P.cst + 5 * D * D;
+        const double* A = cT[t == 0 ? 0 : 1];                 // S0inv or Qinv, A[k * D + c] = M[c][k]
+        const double* Phi = cT[2];
         double col[D];
         double tr = 0.0, trA = 0.0, resid = 0.0;
         if (c < D) {
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 col[k] = Cm[warp][k * D + c];
-                trA = fma(A[c * D + k], col[k], trA);       // sum_k A[c][k] * cov[k][c]
+                trA = fma(A[k * D + c], col[k], trA);       // sum_k A[c][k] * cov[k][c]
                 tr = (k == c) ? col[k] : tr;
             }
             resid = vec[warp][c];
             if (t > 0) {
                 double pm = 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) pm = fma(Phi[c * D + k], vec[warp][D + k], pm);
+                for (int k = 0; k < D; ++k) pm = fma(Phi[k * D + c], vec[warp][D + k], pm);
                 resid -= pm;
             }
         } else {
@@ -1448,7 +1457,7 @@ __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0
         if (c < D) {
             double a = 0.0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) a = fma(A[c * D + k], vec[warp][k], a);
+            for (int k = 0; k < D; ++k) a = fma(A[k * D + c], vec[warp][k], a);
             quad = resid * a;
         }
         const double logdet = tame_logdet_spd<D>(col, rowb[warp], lane);
