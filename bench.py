@@ -379,6 +379,33 @@ def run_ours(args, shape):
     value = units * args.steps / (ms * 1e-3)
     peak, peak_src = measured_peak()
 
+    # ---- the step after the fit: align the fitted means with the true latents on the device
+    align = None
+    if world == 1 and rank == 0:
+        out_al = torch.empty_like(Xm)
+        mse_al = C.c_double(0.0)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(2 + 5):
+            if rep == 2:
+                a0.record()
+            _lib.check(lib.tame_align_states(n, T, r, Xm.data_ptr(), X.data_ptr(), 1, out_al.data_ptr(), None, None, stream))
+        a1.record()
+        _lib.check(lib.tame_align_states(n, T, r, Xm.data_ptr(), X.data_ptr(), 1, out_al.data_ptr(), None, C.byref(mse_al), stream))
+        al_ms = a0.elapsed_time(a1) / 5
+        al_bytes = 5.0 * n * T * d * 8            # X_est and X_true read twice (cross-covariance, apply), aligned written once
+        align = {"op": "align_temporal_states + alignment error (src/utils/alignment.py:224-385)", "ms": al_ms,
+                 "achieved": al_bytes / (al_ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes": al_bytes,
+                 "mse_after_alignment": mse_al.value}
+        if not args.no_cpu:
+            from oracle import align_oracle
+            xe_h, xt_h = Xm.cpu().numpy(), X.cpu().numpy()
+            t0 = time.time()
+            ref_al = align_oracle.align_temporal_states(xe_h, xt_h, r)
+            align["cpu_port_ms"] = (time.time() - t0) * 1e3
+            align["max_abs_diff_vs_port"] = float(np.max(np.abs(out_al.cpu().numpy() - ref_al)))
+            del xe_h, xt_h, ref_al
+        del out_al
+
     # ---- e2e through host buffers (single GPU): host Y/state -> tame_fit_host -> state back
     e2e = None
     cpu = None
@@ -434,6 +461,8 @@ def run_ours(args, shape):
                          "k_llmse": {"achieved": llmse_gbs, "frac": (llmse_gbs / peak) if llmse_gbs else None}},
             "clocks": clocks, "gpu_launches": int(launches), "elbo_trace_tail": elbos[-2:], "chain_probes": probes,
         }
+        if align:
+            line["align"] = align
         if e2e:
             line["e2e"] = e2e
         if cpu:

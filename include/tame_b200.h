@@ -133,6 +133,27 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
 int tame_generate_Y(int32_t n, int32_t T, int32_t r, const double R[4], const double* X_true_dev, uint64_t seed,
                     int32_t row_begin, int32_t row_end, double* Y_dev, void* cuda_stream);
 
+/* ---- alignment (the step after the fit in every driver: src/utils/alignment.py; demo.py:135-137) ------------ */
+/* align_temporal_states (alignment.py:224-313) fused with the error of compute_alignment_error (:316-385).
+ * X_est, X_true, X_aligned: (n, T, d) device arrays, d = 2 + 2r.
+ *   align_each_time != 0: per time step, (a,b) rows get a sign flip when the flipped row is closer; U and V are each
+ *     rotated by R = U Vt of svd(X_true' X_est) (last singular direction negated if det R < 0, :76-90) and then sign-
+ *     flipped row by row (:204-214).
+ *   align_each_time == 0: one 2r x 2r rotation from the temporal means of the multiplicative block (:286-311).
+ * rot_dev (optional, device): the rotations, (T, 2, r, r) or (2r, 2r).  mse_host (optional, host): mean((X_aligned -
+ * X_true)^2); passing it synchronises the stream.  The same call with T = 1 is the static (n, d) case of
+ * compute_alignment_error (:362-369). */
+int tame_align_states(int32_t n, int32_t T, int32_t r, const double* X_est_dev, const double* X_true_dev,
+                      int32_t align_each_time, double* X_aligned_dev, double* rot_dev, double* mse_host, void* cuda_stream);
+/* align_signs (alignment.py:106-166) on `rows` vectors of `width` entries: a vector is negated when that brings it
+ * strictly closer to its target.  mse_host optional as above. */
+int tame_align_signs(int64_t rows, int32_t width, const double* X_est_dev, const double* X_true_dev, double* X_aligned_dev,
+                     double* mse_host, void* cuda_stream);
+/* procrustes_alignment (alignment.py:31-103) of two (n, k) matrices, k <= 16: X_aligned = X_est R (times the optimal
+ * scale when scaling != 0, :95-101); rot_dev (optional) receives R (k, k). */
+int tame_procrustes(int32_t n, int32_t k, const double* X_est_dev, const double* X_true_dev, int32_t scaling,
+                    double* X_aligned_dev, double* rot_dev, void* cuda_stream);
+
 /* ---- multi GPU ------------------------------------------------------------------------------------------ */
 /* 128-byte NCCL unique id: rank 0 creates it, the caller ships it to the other ranks (torch.distributed),
  * every rank calls tame_comm_init.  After that tame_sweep broadcasts each finished panel's means from its

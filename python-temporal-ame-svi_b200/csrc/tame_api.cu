@@ -34,6 +34,16 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+// error reporting for the other translation units of the library (tame_align.cu)
+int tame_set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
 #define CK(call)                                                                                          \
     do {                                                                                                  \
         cudaError_t e_ = (call);                                                                          \

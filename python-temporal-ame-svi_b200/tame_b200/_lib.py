@@ -54,6 +54,9 @@ SIGNATURES = {
     "tame_fit_batch": (C.c_int, [C.c_int32, C.POINTER(TameConfig), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int32,
                                 C.c_double, _DP, _DP, C.POINTER(C.c_int32), C.c_int32]),
     "tame_generate_Y": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _DP, _P, C.c_uint64, C.c_int32, C.c_int32, _P, _P]),
+    "tame_align_states": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _DP, _P]),
+    "tame_align_signs": (C.c_int, [C.c_int64, C.c_int32, _P, _P, _P, _DP, _P]),
+    "tame_procrustes": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "tame_comm_unique_id": (C.c_int, [_P]),
     "tame_comm_init": (C.c_int, [_P, _P]),
     "tame_ipc_export": (C.c_int, [_P, _P]),
