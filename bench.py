@@ -405,6 +405,35 @@ def run_ours(args, shape):
             align["max_abs_diff_vs_port"] = float(np.max(np.abs(out_al.cpu().numpy() - ref_al)))
             del xe_h, xt_h, ref_al
         del out_al
+        # contribution / U'V diagnostics on the same arrays
+        d_add = torch.empty(T, dtype=torch.float64, device=dev)
+        d_mul = torch.empty(T, dtype=torch.float64, device=dev)
+        d_cor = torch.empty(T, dtype=torch.float64, device=dev)
+        for rep in range(2 + 5):
+            if rep == 2:
+                a0.record()
+            _lib.check(lib.tame_contributions(n, T, r, Xm.data_ptr(), 1, d_add.data_ptr(), d_mul.data_ptr(), stream))
+            _lib.check(lib.tame_uv_correlation(n, T, r, Xm.data_ptr(), X.data_ptr(), d_cor.data_ptr(), stream))
+        a1.record()
+        torch.cuda.synchronize(dev)
+        dg_ms = a0.elapsed_time(a1) / 5
+        dg_bytes = 7.0 * n * T * d * 8            # contributions: X_est twice; correlation: X_est 3x, X_true 2x (row sums + Grams + cross)
+        align["diagnostics"] = {"op": "compute_temporal_contributions + compute_uv_correlation_over_time (diagnostics.py:170-217, multiplicative_strength_comparison.py:46-89)",
+                                "ms": dg_ms, "achieved": dg_bytes / (dg_ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes": dg_bytes,
+                                "uv_corr_t0": float(d_cor[0].item())}
+        if not args.no_cpu:
+            from oracle import diag_oracle
+            ts = [0, T - 1]
+            xe_h, xt_h = Xm[:, ts].cpu().numpy(), X[:, ts].cpu().numpy()
+            t0 = time.time()
+            o_add, o_mul = diag_oracle.temporal_contributions(xe_h, r, True)
+            o_cor = diag_oracle.uv_correlation_over_time(xe_h, xt_h, r)
+            align["diagnostics"]["cpu_port_ms"] = (time.time() - t0) * 1e3 * T / len(ts)
+            align["diagnostics"]["cpu_port_sample"] = f"{len(ts)} of {T} time steps, scaled"
+            align["diagnostics"]["max_abs_diff_vs_port"] = float(max(np.max(np.abs(d_add[ts].cpu().numpy() - o_add)),
+                                                                       np.max(np.abs(d_mul[ts].cpu().numpy() - o_mul)),
+                                                                       np.max(np.abs(d_cor[ts].cpu().numpy() - o_cor))))
+            del xe_h, xt_h
 
     # ---- e2e through host buffers (single GPU): host Y/state -> tame_fit_host -> state back
     e2e = None

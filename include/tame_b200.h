@@ -154,6 +154,20 @@ int tame_align_signs(int64_t rows, int32_t width, const double* X_est_dev, const
 int tame_procrustes(int32_t n, int32_t k, const double* X_est_dev, const double* X_true_dev, int32_t scaling,
                     double* X_aligned_dev, double* rot_dev, void* cuda_stream);
 
+/* ---- diagnostics (src/utils/diagnostics.py; experiments/multiplicative_strength_comparison.py:46-89) ------------- */
+/* compute_temporal_contributions (diagnostics.py:170-217): per time step the mean over node pairs of (a_i + b_j)^2
+ * (compute_additive_contribution :82-122) and of (U_i . V_j)^2 (compute_multiplicative_contribution :125-167), with or
+ * without the diagonal pairs.  X (n, T, d) device; additive_dev / multiplicative_dev: T doubles, device. */
+int tame_contributions(int32_t n, int32_t T, int32_t r, const double* X_dev, int32_t exclude_diagonal, double* additive_dev,
+                       double* multiplicative_dev, void* cuda_stream);
+/* compute_uv_correlation_over_time (multiplicative_strength_comparison.py:46-89) / compute_uv_product_correlation
+ * (diagnostics.py:528-561, T = 1): Pearson correlation of the flattened n x n products U V' of the estimate and of the
+ * truth, per time step.  corr_dev: T doubles, device. */
+int tame_uv_correlation(int32_t n, int32_t T, int32_t r, const double* X_est_dev, const double* X_true_dev, double* corr_dev,
+                        void* cuda_stream);
+/* compute_state_prediction_error (diagnostics.py:254-273): mean((A - B)^2) over `count` doubles.  Synchronises. */
+int tame_state_mse(int64_t count, const double* A_dev, const double* B_dev, double* mse_host, void* cuda_stream);
+
 /* ---- multi GPU ------------------------------------------------------------------------------------------ */
 /* 128-byte NCCL unique id: rank 0 creates it, the caller ships it to the other ranks (torch.distributed),
  * every rank calls tame_comm_init.  After that tame_sweep broadcasts each finished panel's means from its

@@ -469,6 +469,140 @@ __global__ void k_align_scale(double* __restrict__ X, long count, const double* 
     if (e < count) X[e] *= s;
 }
 
+// ---- contribution / U'V-product diagnostics (src/utils/diagnostics.py:82-217,528-561) -----------------------------------
+// The reference forms the n x n matrices a_i + b_j and U_i.V_j per time step.  Their sums of squares and products follow
+// from r x r Gram matrices (the same DMMA kernel as the alignment) and a few per-time-step row sums:
+//   sum_ij (a_i + b_j)^2   = n sum a^2 + n sum b^2 + 2 (sum a)(sum b)          diagonal: sum_i (a_i + b_i)^2
+//   sum_ij (U_i.V_j)^2     = <U'U, V'V>                                        diagonal: sum_i (U_i.V_i)^2
+//   sum_ij (U_i.V_j)       = (sum_i U_i).(sum_j V_j)
+//   sum_ij (Ut_i.Vt_j)(Ue_i.Ve_j) = <Ut'Ue, Vt'Ve>
+constexpr int DQ = 6;      // scalar row sums: sum a, sum b, sum a^2, sum b^2, sum (a+b)^2, sum (U.V)^2; then sum U (r), sum V (r)
+
+// grid (ceil(T/32), NI), 128 threads: lane = time step, the four warps walk over nodes; every lane keeps the sums of its
+// own time step, so there is no cross-lane reduction.  partial[((blockIdx.y*4 + warp) * T + t) * (DQ + 2R) + q]
+template <int R>
+__global__ void __launch_bounds__(128) k_diag_rows(const double* __restrict__ X, int n, int T, double* __restrict__ partial) {
+    constexpr int D = 2 + 2 * R, NQ = DQ + 2 * R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    if (t >= T) return;
+    const int per = (n + gridDim.y - 1) / gridDim.y;
+    const int ibeg = blockIdx.y * per, iend = min(n, ibeg + per);
+    double q[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) q[k] = 0.0;
+    for (int i = ibeg + warp; i < iend; i += 4) {
+        const double* x = X + ((size_t)i * T + t) * D;
+        const double a = x[0], b = x[1];
+        q[0] += a;
+        q[1] += b;
+        q[2] = fma(a, a, q[2]);
+        q[3] = fma(b, b, q[3]);
+        q[4] = fma(a + b, a + b, q[4]);
+        double uv = 0.0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const double u = x[2 + k], v = x[2 + R + k];
+            uv = fma(u, v, uv);
+            q[DQ + k] += u;
+            q[DQ + R + k] += v;
+        }
+        q[5] = fma(uv, uv, q[5]);
+    }
+    double* out = partial + ((size_t)(blockIdx.y * 4 + warp) * T + t) * NQ;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) out[k] = q[k];
+}
+
+// sums[t][q] = fixed-order sum over the (block, warp) slots
+__global__ void k_diag_rows_reduce(const double* __restrict__ partial, int nslots, int T, int NQ, double* __restrict__ sums) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * NQ) return;
+    double v = 0.0;
+    for (int s = 0; s < nslots; ++s) v += partial[(size_t)s * T * NQ + e];
+    sums[e] = v;
+}
+
+// one thread per time step.  gram: (T, 2, r, r) = U'U, V'V of X.
+__global__ void k_diag_contrib(const double* __restrict__ sums, const double* __restrict__ gram, int n, int T, int r,
+                               int exclude_diagonal, double* __restrict__ additive, double* __restrict__ multiplicative) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const double* q = sums + (size_t)t * (DQ + 2 * r);
+    const double nn = (double)n;
+    double add = nn * q[2] + nn * q[3] + 2.0 * q[0] * q[1];
+    double mul = 0.0;
+    const double* gu = gram + (size_t)t * 2 * r * r;
+    const double* gv = gu + r * r;
+    for (int e = 0; e < r * r; ++e) mul = fma(gu[e], gv[e], mul);
+    double cnt = nn * nn;
+    if (exclude_diagonal) {
+        add -= q[4];
+        mul -= q[5];
+        cnt = nn * (nn - 1.0);
+    }
+    additive[t] = add / cnt;
+    multiplicative[t] = mul / cnt;
+}
+
+// Pearson correlation of the flattened n x n products U V' (diagonal included), one thread per time step.
+__global__ void k_diag_corr(const double* __restrict__ sums_e, const double* __restrict__ sums_t, const double* __restrict__ gram_e,
+                            const double* __restrict__ gram_t, const double* __restrict__ cross, int n, int T, int r,
+                            double* __restrict__ corr) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int NQ = DQ + 2 * r, rr = r * r;
+    const double* qe = sums_e + (size_t)t * NQ;
+    const double* qt = sums_t + (size_t)t * NQ;
+    double se = 0.0, st = 0.0;
+    for (int k = 0; k < r; ++k) {
+        se = fma(qe[DQ + k], qe[DQ + r + k], se);
+        st = fma(qt[DQ + k], qt[DQ + r + k], st);
+    }
+    double see = 0.0, stt = 0.0, ste = 0.0;
+    const double* ge = gram_e + (size_t)t * 2 * rr;
+    const double* gt = gram_t + (size_t)t * 2 * rr;
+    const double* gx = cross + (size_t)t * 2 * rr;
+    for (int e = 0; e < rr; ++e) {
+        see = fma(ge[e], ge[rr + e], see);
+        stt = fma(gt[e], gt[rr + e], stt);
+        ste = fma(gx[e], gx[rr + e], ste);
+    }
+    const double N = (double)n * (double)n;
+    double c = 0.0;
+    if (N > 1.0) {                                   // multiplicative_strength_comparison.py:82-86
+        const double cov = ste - st * se / N, ve = see - se * se / N, vt = stt - st * st / N;
+        c = cov / sqrt(ve * vt);
+        c = fmin(1.0, fmax(-1.0, c));                // torch.corrcoef clips to [-1, 1]
+    }
+    corr[t] = c;
+}
+
+__global__ void k_diag_sqdiff(const double* __restrict__ A, const double* __restrict__ B, long count, double* __restrict__ partial) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) {
+        const double df = A[e] - B[e];
+        s = fma(df, df, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+        partial[blockIdx.x] = v;
+    }
+}
+
+template <int R>
+void launch_diag_rows(dim3 grid, cudaStream_t st, const double* X, int n, int T, double* partial) {
+    k_diag_rows<R><<<grid, 128, 0, st>>>(X, n, T, partial);
+}
+
+// row sums + Gram matrices of one state array: sums (T, DQ+2r), gram (T, 2, r, r); scratch is freed stream-ordered
+int diag_moments(int n, int T, int r, const double* X, double* sums, double* gram, cudaStream_t st);
+
 int split_rows(int n, int T) {
     // enough (time step, row split) blocks to keep every SM busy with the latency-bound accumulation, >= 64 rows each
     int ns = (4736 + T - 1) / T;            // ~32 blocks per SM
@@ -606,3 +740,105 @@ extern "C" int tame_procrustes(int32_t n, int32_t k, const double* X_est_dev, co
     ACK(cudaFreeAsync(numden, st));
     return TAME_OK;
 }
+
+namespace {
+int diag_cross(int n, int T, int r, const double* est, const double* tru, double* out, cudaStream_t st) {
+    // out (T, 2, r, r) = [X_true_U' X_est_U, X_true_V' X_est_V] per time step
+    const int d = 2 + 2 * r, NS = split_rows(n, T), kk = r * r;
+    double* partial = nullptr;
+    ACK(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)T * NS * 2 * kk, st));
+    k_align_cross<<<dim3(T, NS), 128, 0, st>>>(est, tru, n, T, d, 2, r, 2, partial);
+    k_align_reduce<<<(T * 2 * kk + 255) / 256, 256, 0, st>>>(partial, T * 2, 2, NS, kk, out);
+    tame_count_launch(2);
+    ACK(cudaFreeAsync(partial, st));
+    return TAME_OK;
+}
+
+int diag_moments(int n, int T, int r, const double* X, double* sums, double* gram, cudaStream_t st) {
+    const int NQ = DQ + 2 * r, nbx = (T + 31) / 32;
+    int nby = (148 * 8 + nbx - 1) / nbx;
+    if (nby > (n + 3) / 4) nby = (n + 3) / 4;
+    if (nby < 1) nby = 1;
+    double* partial = nullptr;
+    const size_t pbytes = sizeof(double) * (size_t)nby * 4 * T * NQ;
+    ACK(cudaMallocAsync((void**)&partial, pbytes, st));
+    ACK(cudaMemsetAsync(partial, 0, pbytes, st));        // slots of warps without rows stay zero
+    const dim3 grid(nbx, nby);
+    switch (r) {
+        case 1: launch_diag_rows<1>(grid, st, X, n, T, partial); break;
+        case 2: launch_diag_rows<2>(grid, st, X, n, T, partial); break;
+        case 3: launch_diag_rows<3>(grid, st, X, n, T, partial); break;
+        case 4: launch_diag_rows<4>(grid, st, X, n, T, partial); break;
+        case 5: launch_diag_rows<5>(grid, st, X, n, T, partial); break;
+        case 6: launch_diag_rows<6>(grid, st, X, n, T, partial); break;
+        case 7: launch_diag_rows<7>(grid, st, X, n, T, partial); break;
+        default: launch_diag_rows<8>(grid, st, X, n, T, partial); break;
+    }
+    k_diag_rows_reduce<<<(T * NQ + 255) / 256, 256, 0, st>>>(partial, nby * 4, T, NQ, sums);
+    tame_count_launch(2);
+    ACK(cudaFreeAsync(partial, st));
+    if (gram) return diag_cross(n, T, r, X, X, gram, st);
+    return TAME_OK;
+}
+}  // namespace
+
+extern "C" int tame_contributions(int32_t n, int32_t T, int32_t r, const double* X_dev, int32_t exclude_diagonal,
+                                  double* additive_dev, double* multiplicative_dev, void* cuda_stream) {
+    if (n < 1 || T < 1) return tame_set_error(TAME_EINVAL, "tame_contributions: n and T must be positive");
+    if (r < 1 || r > TAME_MAX_R) return tame_set_error(TAME_EINVAL, "tame_contributions: latent_dim must be 1..%d", TAME_MAX_R);
+    if (!X_dev || !additive_dev || !multiplicative_dev) return tame_set_error(TAME_EINVAL, "tame_contributions: null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    double *sums = nullptr, *gram = nullptr;
+    ACK(cudaMallocAsync((void**)&sums, sizeof(double) * (size_t)T * (DQ + 2 * r), st));
+    ACK(cudaMallocAsync((void**)&gram, sizeof(double) * (size_t)T * 2 * r * r, st));
+    int rc = diag_moments(n, T, r, X_dev, sums, gram, st);
+    if (rc != TAME_OK) return rc;
+    k_diag_contrib<<<(T + 127) / 128, 128, 0, st>>>(sums, gram, n, T, r, exclude_diagonal ? 1 : 0, additive_dev, multiplicative_dev);
+    tame_count_launch(1);
+    ACK(cudaGetLastError());
+    ACK(cudaFreeAsync(sums, st));
+    ACK(cudaFreeAsync(gram, st));
+    return TAME_OK;
+}
+
+extern "C" int tame_uv_correlation(int32_t n, int32_t T, int32_t r, const double* X_est_dev, const double* X_true_dev,
+                                   double* corr_dev, void* cuda_stream) {
+    if (n < 1 || T < 1) return tame_set_error(TAME_EINVAL, "tame_uv_correlation: n and T must be positive");
+    if (r < 1 || r > TAME_MAX_R) return tame_set_error(TAME_EINVAL, "tame_uv_correlation: latent_dim must be 1..%d", TAME_MAX_R);
+    if (!X_est_dev || !X_true_dev || !corr_dev) return tame_set_error(TAME_EINVAL, "tame_uv_correlation: null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t ns = (size_t)T * (DQ + 2 * r), ng = (size_t)T * 2 * r * r;
+    double* buf = nullptr;
+    ACK(cudaMallocAsync((void**)&buf, sizeof(double) * (2 * ns + 3 * ng), st));
+    double *sums_e = buf, *sums_t = buf + ns, *gram_e = buf + 2 * ns, *gram_t = gram_e + ng, *cross = gram_t + ng;
+    int rc = diag_moments(n, T, r, X_est_dev, sums_e, gram_e, st);
+    if (rc == TAME_OK) rc = diag_moments(n, T, r, X_true_dev, sums_t, gram_t, st);
+    if (rc == TAME_OK) rc = diag_cross(n, T, r, X_est_dev, X_true_dev, cross, st);
+    if (rc != TAME_OK) return rc;
+    k_diag_corr<<<(T + 127) / 128, 128, 0, st>>>(sums_e, sums_t, gram_e, gram_t, cross, n, T, r, corr_dev);
+    tame_count_launch(1);
+    ACK(cudaGetLastError());
+    ACK(cudaFreeAsync(buf, st));
+    return TAME_OK;
+}
+
+extern "C" int tame_state_mse(int64_t count, const double* A_dev, const double* B_dev, double* mse_host, void* cuda_stream) {
+    if (count < 1 || !A_dev || !B_dev || !mse_host) return tame_set_error(TAME_EINVAL, "tame_state_mse: bad argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    long nb = (count + 2047) / 2048;
+    if (nb > 148 * 8) nb = 148 * 8;
+    double *partial = nullptr, *mse = nullptr;
+    ACK(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)nb, st));
+    ACK(cudaMallocAsync((void**)&mse, sizeof(double), st));
+    k_diag_sqdiff<<<(unsigned)nb, 256, 0, st>>>(A_dev, B_dev, count, partial);
+    k_align_sum<<<1, 256, 0, st>>>(partial, nb, 1, 1.0 / (double)count, mse);
+    tame_count_launch(2);
+    double host = 0.0;
+    ACK(cudaMemcpyAsync(&host, mse, sizeof(double), cudaMemcpyDeviceToHost, st));
+    ACK(cudaFreeAsync(partial, st));
+    ACK(cudaFreeAsync(mse, st));
+    ACK(cudaStreamSynchronize(st));
+    *mse_host = host;
+    return TAME_OK;
+}
+

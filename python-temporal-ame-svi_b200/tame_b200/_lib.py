@@ -57,6 +57,9 @@ SIGNATURES = {
     "tame_align_states": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _DP, _P]),
     "tame_align_signs": (C.c_int, [C.c_int64, C.c_int32, _P, _P, _P, _DP, _P]),
     "tame_procrustes": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
+    "tame_contributions": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P]),
+    "tame_uv_correlation": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "tame_state_mse": (C.c_int, [C.c_int64, _P, _P, _DP, _P]),
     "tame_comm_unique_id": (C.c_int, [_P]),
     "tame_comm_init": (C.c_int, [_P, _P]),
     "tame_ipc_export": (C.c_int, [_P, _P]),
