@@ -212,7 +212,25 @@ __device__ __forceinline__ void tame_stream_cols(const TameParams& P, unsigned c
             tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
         }
     };
+    // fast path of the record staging: with the natural record pitch (RS == D) and a full 32-step slice, partner j's records
+    // are one contiguous block of 32*D doubles in global AND shared memory, so 16-byte piece e of the chunk goes from
+    // base + 2e + jj*(T*D - 32*D) to Mb[buf] + 2e with jj = e / (32*PIECES): no per-piece modulo / clamp / predicate.
+    const bool m_fast = (RS == D) && (t0 + 32 <= P.T);
+    const size_t m_gap = (size_t)P.T * D - 32 * D;
     auto issue_m = [&](int buf, int jc) {
+        if (m_fast && jc + JC <= P.n) {
+            const double* base = P.Xm + ((size_t)jc * P.T + t0) * D;
+            double* dst = &Mb[buf][0][0][0];
+#pragma unroll
+            for (int it = 0; it < (JC * 32 * TS::PIECES + 255) / 256; ++it) {
+                const int e = tid + it * 256;
+                if ((it + 1) * 256 <= JC * 32 * TS::PIECES || e < JC * 32 * TS::PIECES) {
+                    const int jj = e / (32 * TS::PIECES);
+                    tame_cp_async16(dst + 2 * e, base + 2 * e + jj * m_gap, true);
+                }
+            }
+            return;
+        }
         for (int e = tid; e < JC * 32 * TS::PIECES; e += 256) {
             const int piece = e % TS::PIECES, tl = (e / TS::PIECES) & 31, jj = e / (TS::PIECES * 32);
             const int j = jc + jj, tt = t0 + tl;
@@ -1111,7 +1129,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_llmse(TameParams P, double* part
             tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
         }
     };
+    // fast path of the record staging (see tame_stream_cols)
+    const bool m_fast = (RS == D) && (t0 + 32 <= P.T);
+    const size_t m_gap = (size_t)P.T * D - 32 * D;
     auto issue_m = [&](int buf, int jc) {
+        if (m_fast && jc + JC <= P.n) {
+            const double* base = P.Xm + ((size_t)jc * P.T + t0) * D;
+            double* dst = &Mb[buf][0][0][0];
+#pragma unroll
+            for (int it = 0; it < (JC * 32 * TS::PIECES + NT - 1) / NT; ++it) {
+                const int e = tid + it * NT;
+                if ((it + 1) * NT <= JC * 32 * TS::PIECES || e < JC * 32 * TS::PIECES) {
+                    const int jj = e / (32 * TS::PIECES);
+                    tame_cp_async16(dst + 2 * e, base + 2 * e + jj * m_gap, true);
+                }
+            }
+            return;
+        }
         for (int e = tid; e < JC * 32 * TS::PIECES; e += NT) {
             const int piece = e % TS::PIECES, tl = (e / TS::PIECES) & 31, jj = e / (TS::PIECES * 32);
             const int j = jc + jj, tt = t0 + tl;
