@@ -222,7 +222,7 @@ def make_cfg(lib_mod, c, n, T, r, device, world, rank):
     return cfg, keep
 
 
-def hyper_constants(n, T, r):
+def hyper_constants(n, T, r, ar=None, rho=None):
     """Same hyper-parameters as TemporalAMEModel builds (static_ame.py:96-127, temporal_ame.py:129-145); computed with
     numpy here so bench.py's GPU arm does not import the oracle."""
     d = 2 + 2 * r
@@ -231,12 +231,12 @@ def hyper_constants(n, T, r):
         m = np.full((dim, dim), corr * var)
         np.fill_diagonal(m, var)
         return m
-    R = eq(2, HYPER["rho_dyadic"], 0.1)
+    R = eq(2, HYPER["rho_dyadic"] if rho is None else rho, 0.1)
     S0 = np.zeros((d, d))
     S0[:2, :2] = eq(2, HYPER["rho_additive"], 1.0)
     S0[2:2 + r, 2:2 + r] = eq(r, HYPER["rho_multiplicative"], 1.0)
     S0[2 + r:, 2 + r:] = eq(r, HYPER["rho_multiplicative"], 1.0)
-    phi = HYPER["ar_coefficient"]
+    phi = HYPER["ar_coefficient"] if ar is None else ar
     Q = (1 - phi ** 2) * S0 * 0.1
     return dict(n=n, T=T, r=r, d=d, R=R, R_inv=np.linalg.inv(R), S0=S0, S0_inv=np.linalg.inv(S0), Q=Q, Q_inv=np.linalg.inv(Q),
                 Phi=np.eye(d) * phi, logdet_R=np.linalg.slogdet(R)[1], logdet_Q=np.linalg.slogdet(Q)[1],
