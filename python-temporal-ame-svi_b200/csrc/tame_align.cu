@@ -514,13 +514,16 @@ __global__ void __launch_bounds__(128) k_diag_rows(const double* __restrict__ X,
     for (int k = 0; k < NQ; ++k) out[k] = q[k];
 }
 
-// sums[t][q] = fixed-order sum over the (block, warp) slots
-__global__ void k_diag_rows_reduce(const double* __restrict__ partial, int nslots, int T, int NQ, double* __restrict__ sums) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// sums[t][q] = sum over the (block, warp) slots: one warp per output element, lanes stride over the slots and combine by
+// shuffles -- a fixed order, so the result is reproducible
+__global__ void __launch_bounds__(128) k_diag_rows_reduce(const double* __restrict__ partial, int nslots, int T, int NQ,
+                                                          double* __restrict__ sums) {
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (e >= T * NQ) return;
     double v = 0.0;
-    for (int s = 0; s < nslots; ++s) v += partial[(size_t)s * T * NQ + e];
-    sums[e] = v;
+    for (int s = lane; s < nslots; s += 32) v += partial[(size_t)s * T * NQ + e];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sums[e] = v;
 }
 
 // one thread per time step.  gram: (T, 2, r, r) = U'U, V'V of X.
@@ -774,7 +777,7 @@ int diag_moments(int n, int T, int r, const double* X, double* sums, double* gra
         case 7: launch_diag_rows<7>(grid, st, X, n, T, partial); break;
         default: launch_diag_rows<8>(grid, st, X, n, T, partial); break;
     }
-    k_diag_rows_reduce<<<(T * NQ + 255) / 256, 256, 0, st>>>(partial, nby * 4, T, NQ, sums);
+    k_diag_rows_reduce<<<(T * NQ + 3) / 4, 128, 0, st>>>(partial, nby * 4, T, NQ, sums);
     tame_count_launch(2);
     ACK(cudaFreeAsync(partial, st));
     if (gram) return diag_cross(n, T, r, X, X, gram, st);

@@ -6,6 +6,8 @@
 #include <nccl.h>
 
 #include <atomic>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -683,67 +685,54 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
     if (n_fits < 0 || (n_fits > 0 && (!cfgs || !Y_dev || !Xm_dev || !Xc_dev || !n_done))) return fail(TAME_EINVAL, "null argument");
     if (n_streams <= 0) n_streams = 8;
     n_streams = std::min(n_streams, std::max(n_fits, 1));
-    // one worker slot per stream: each slot drives one fit at a time, iteration by iteration; slots are advanced
-    // round-robin so the (small) kernels of different fits overlap on the device
-    struct Slot { tame_handle* h = nullptr; int fit = -1, it = 0, patience = 0; double prev = -INFINITY; cudaStream_t st = nullptr; };
-    std::vector<Slot> slots(n_streams);
-    for (auto& s : slots) CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-    int next = 0, active = 0, rc = TAME_OK;
-    auto start = [&](Slot& s) -> int {
-        while (next < n_fits) {
-            const int f = next++;
-            n_done[f] = 0;
-            if (max_iter <= 0) continue;
-            int r = tame_create(&cfgs[f], &s.h);
-            if (r != TAME_OK) return r;
-            tame_set_stream(s.h, s.st);
-            r = tame_bind_Y(s.h, Y_dev[f]);
-            if (r == TAME_OK) r = tame_bind_state(s.h, Xm_dev[f], Xc_dev[f]);
-            if (r != TAME_OK) return r;
-            s.fit = f; s.it = 0; s.patience = 0; s.prev = -INFINITY;
-            ++active;
-            return TAME_OK;
+    for (int f = 0; f < n_fits; ++f) n_done[f] = 0;
+    if (max_iter <= 0 || n_fits == 0) return TAME_OK;
+    // Small fits are bound by the host's launch rate, not by the device: one host thread per stream, each taking the next
+    // unstarted fit and running the loop of base.py:166-203 on its own handle and stream.  Kernels of different fits
+    // overlap on the device; nothing is shared between the workers but the fit counter.
+    std::atomic<int> next{0};
+    std::atomic<int> first_rc{TAME_OK};
+    std::mutex err_mu;
+    std::string err_msg;
+    auto worker = [&]() {
+        cudaStream_t st = nullptr;
+        int rc = TAME_OK;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = fail(TAME_ECUDA, "cudaStreamCreate failed in tame_fit_batch");
+        while (rc == TAME_OK && first_rc.load() == TAME_OK) {
+            const int f = next.fetch_add(1);
+            if (f >= n_fits) break;
+            tame_handle* h = nullptr;
+            rc = tame_create(&cfgs[f], &h);
+            if (rc == TAME_OK) rc = tame_set_stream(h, st);
+            if (rc == TAME_OK) rc = tame_bind_Y(h, Y_dev[f]);
+            if (rc == TAME_OK) rc = tame_bind_state(h, Xm_dev[f], Xc_dev[f]);
+            if (rc == TAME_OK)
+                rc = tame_fit(h, max_iter, tolerance, elbo_traces ? elbo_traces + (size_t)f * max_iter : nullptr,
+                              mse_traces ? mse_traces + (size_t)f * max_iter : nullptr, &n_done[f]);
+            if (h) {
+                std::string keep = g_err;
+                tame_destroy(h);
+                g_err = keep;
+            }
         }
-        s.fit = -1;
-        return TAME_OK;
+        if (rc != TAME_OK) {
+            int expected = TAME_OK;
+            if (first_rc.compare_exchange_strong(expected, rc)) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                err_msg = g_err;
+            }
+        }
+        if (st) cudaStreamDestroy(st);
     };
-    for (auto& s : slots) { rc = start(s); if (rc != TAME_OK) break; }
-    while (rc == TAME_OK && active > 0) {
-        // enqueue one sweep on every active slot, then collect the ELBO/MSE of each (tame_elbo_mse synchronises its stream)
-        for (auto& s : slots) if (s.fit >= 0) { rc = tame_sweep(s.h); if (rc != TAME_OK) break; }
-        if (rc != TAME_OK) break;
-        for (auto& s : slots) {
-            if (s.fit < 0) continue;
-            double o[6];
-            rc = tame_elbo_mse(s.h, o);
-            if (rc != TAME_OK) break;
-            const int f = s.fit;
-            if (elbo_traces) elbo_traces[(size_t)f * max_iter + s.it] = o[0];
-            if (mse_traces) mse_traces[(size_t)f * max_iter + s.it] = o[5];
-            bool converged = false;
-            if (s.it > 0) {
-                const double rel = std::fabs(o[0] - s.prev) / (std::fabs(s.prev) + 1e-8);
-                s.patience = (rel < tolerance) ? s.patience + 1 : 0;
-                converged = s.patience >= 3;
-            }
-            s.prev = o[0];
-            n_done[f] = ++s.it;
-            if (converged || s.it >= max_iter) {
-                tame_destroy(s.h);
-                s.h = nullptr;
-                --active;
-                rc = start(s);
-                if (rc != TAME_OK) break;
-            }
-        }
+    std::vector<std::thread> pool;
+    for (int w = 1; w < n_streams; ++w) pool.emplace_back(worker);
+    worker();                                   // the calling thread is worker 0
+    for (auto& t : pool) t.join();
+    if (first_rc.load() != TAME_OK) {
+        g_err = err_msg;
+        return first_rc.load();
     }
-    std::string keep = g_err;
-    for (auto& s : slots) {
-        if (s.h) tame_destroy(s.h);
-        cudaStreamDestroy(s.st);
-    }
-    g_err = keep;
-    return rc;
+    return TAME_OK;
 }
 
 int tame_generate_Y(int32_t n, int32_t T, int32_t r, const double R[4], const double* X_dev, uint64_t seed,

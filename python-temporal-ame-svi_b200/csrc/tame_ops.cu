@@ -68,8 +68,13 @@ cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
     TameParams p = P;
     p.n_chain_ctas = (P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC;
     const int nunits = ((P.n + TAME_SB - 1) / TAME_SB) * ((P.T + 31) / 32) * P.nparts;
-    const int workers = capacity - p.n_chain_ctas < nunits ? capacity - p.n_chain_ctas : nunits;
+    int workers = capacity - p.n_chain_ctas < nunits ? capacity - p.n_chain_ctas : nunits;
     if (workers < 1) return cudaErrorLaunchOutOfResources;
+    // small problems: the chain (n nodes x ~4 us) outlasts the streaming (16 n^2 T bytes at ~30 GB/s per CTA) unless there are
+    // fewer than ~n T / 7500 streaming CTAs; do not occupy more SMs than that, so that independent fits (tame_fit_batch) run
+    // side by side.  Any count >= 1 is correct: units are claimed dynamically and in order.
+    const long want = ((long)P.n * P.T + 4999) / 5000 + 1;
+    if ((long)workers > want) workers = (int)want;
     void* args[] = {(void*)&p};
     tame_count_launch(1);
     return cudaLaunchCooperativeKernel((void*)k_sweep<R, RW>, dim3(p.n_chain_ctas + workers), dim3(256), args, sweep_smem_bytes(), st);
