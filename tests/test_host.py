@@ -106,6 +106,27 @@ def test_no_cpu_fallback_without_gpu():
         vi.fit(max_iter=1, verbose=False)
 
 
+def test_post_fit_utilities_have_no_cpu_fallback_and_keep_reference_names():
+    """src.utils mirrors the reference's alignment / diagnostics names (src/utils/__init__.py:30-50); without a GPU
+    they raise instead of computing on the host."""
+    import src.utils as U
+    for name in ("procrustes_alignment", "align_signs", "align_latent_positions", "align_temporal_states",
+                 "compute_alignment_error", "compute_correlation_after_alignment", "compute_additive_contribution",
+                 "compute_multiplicative_contribution", "compute_temporal_contributions", "compute_contribution_ratio",
+                 "compute_state_prediction_error", "compute_uv_product_correlation"):
+        assert callable(getattr(U, name)), name
+    x = torch.zeros(4, 3, 6)
+    with pytest.raises(ValueError):                      # alignment.py:354-357: checked before any device work
+        U.compute_alignment_error(x, x)
+    err, same = U.compute_alignment_error(x, x + 1.0, latent_dim=2, align=False)      # no alignment -> plain MSE
+    assert same is x and err == 1.0
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            U.align_temporal_states(x, x, latent_dim=2)
+        with pytest.raises(RuntimeError):
+            U.compute_temporal_contributions(x, 2)
+
+
 def test_library_exports_every_declared_symbol():
     from tame_b200 import _lib
     header = open(os.path.join(ROOT, "include", "tame_b200.h")).read()
