@@ -294,10 +294,24 @@ __global__ void __launch_bounds__(128) k_align_apply(const double* __restrict__ 
     const double* y = sy + lane * DP;
     for (int i = ibeg + warp; i < iend; i += 4) {
         const size_t base = ((size_t)i * T + t0) * D;
-        for (int e = lane; e < nt * D; e += 32) {
-            const int row = e / D, c = e - row * D;
-            se[row * DP + c] = est[base + e];
-            sy[row * DP + c] = tru[base + e];
+        {   // all 2*D loads of the lane are issued before the first shared-memory store (one DRAM round trip, not D)
+            double ve[D], vy[D];
+#pragma unroll
+            for (int it = 0; it < D; ++it) {
+                const int e = lane + 32 * it;
+                const bool in = e < nt * D;
+                ve[it] = in ? est[base + e] : 0.0;
+                vy[it] = in ? tru[base + e] : 0.0;
+            }
+#pragma unroll
+            for (int it = 0; it < D; ++it) {
+                const int e = lane + 32 * it;
+                if (e < nt * D) {
+                    const int row = e / D, c = e - row * D;
+                    se[row * DP + c] = ve[it];
+                    sy[row * DP + c] = vy[it];
+                }
+            }
         }
         __syncwarp();
         if (lane < nt) {
@@ -343,9 +357,13 @@ __global__ void __launch_bounds__(128) k_align_apply(const double* __restrict__ 
             }
         }
         __syncwarp();
-        for (int e = lane; e < nt * D; e += 32) {
-            const int row = e / D, c = e - row * D;
-            out[base + e] = se[row * DP + c];
+#pragma unroll
+        for (int it = 0; it < D; ++it) {
+            const int e = lane + 32 * it;
+            if (e < nt * D) {
+                const int row = e / D, c = e - row * D;
+                out[base + e] = se[row * DP + c];
+            }
         }
         __syncwarp();
     }
