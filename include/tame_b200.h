@@ -119,7 +119,9 @@ int tame_fit_host(const tame_config* cfg, const double* Y_host, double* X_mean_h
  * and method): n_fits independent problems, each with its own tame_config and device buffers (Y_dev[f] is (n,n,T,2),
  * X_mean_dev[f] (n,T,d), X_cov_dev[f] (n,T,d,d), updated in place).  Traces are host arrays of n_fits * max_iter
  * doubles (row f = fit f); n_done[f] = iterations performed by fit f (early stop per fit, base.py:183-203).
- * Fits are independent Gauss-Seidel chains, so they run concurrently on `n_streams` CUDA streams (0 = default 8). */
+ * Fits are independent Gauss-Seidel chains, so they run concurrently on `n_streams` CUDA streams (0 = default 8), each
+ * driven by its own host thread inside the call (the caller's thread is one of them; the call returns when all fits
+ * are done). */
 int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* X_mean_dev,
                    double* const* X_cov_dev, int32_t max_iter, double tolerance, double* elbo_traces_host,
                    double* mse_traces_host, int32_t* n_done, int32_t n_streams);
