@@ -376,12 +376,10 @@ __global__ void __launch_bounds__(128) k_align_apply(const double* __restrict__ 
 template <int R, bool EACH>
 cudaError_t launch_apply_t(dim3 grid, cudaStream_t st, const double* est, const double* tru, int n, int T, const double* rot,
                            double* out, double* partial) {
-    static bool configured = false;
     constexpr size_t smem = AlignSmem<R, EACH>::BYTES;
-    if (!configured) {
+    {   // per-device attribute, set on every call (cheap next to the launch; no per-process flag to go stale on a second GPU)
         cudaError_t e = cudaFuncSetAttribute(k_align_apply<R, EACH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     k_align_apply<R, EACH><<<grid, 128, smem, st>>>(est, tru, n, T, rot, out, partial);
     return cudaSuccess;

@@ -113,7 +113,7 @@ struct tame_handle {
     int* sym_flag = nullptr;
     int* cursor = nullptr;
     // device scratch
-    double *H = nullptr, *hab = nullptr, *tot = nullptr, *tot_partial = nullptr, *cst = nullptr;
+    double *Craw = nullptr, *H = nullptr, *hab = nullptr, *tot = nullptr, *tot_partial = nullptr, *cst = nullptr;
     double *part_ll = nullptr, *part_cell = nullptr, *red6 = nullptr, *out6 = nullptr;
     int *progress = nullptr, *abort_flag = nullptr, *unit_counter = nullptr, *unit_done = nullptr;
     int epoch = 0, nparts = 1;
@@ -401,6 +401,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     h->nparts = (n >= 2048) ? 4 : 1;
     if (const char* v = getenv("TAME_NPARTS")) h->nparts = std::max(1, std::min(TAME_MAX_PARTS, atoi(v)));
     if (e == cudaSuccess) e = dalloc((void**)&h->H, sizeof(double) * (size_t)nloc * T * 2 * cfg->r * h->nparts);
+    if (e == cudaSuccess) e = dalloc((void**)&h->Craw, sizeof(double) * (size_t)nloc * T * d * d);
     if (e == cudaSuccess) e = dalloc((void**)&h->hab, sizeof(double) * (size_t)nloc * T * 2);
     if (e == cudaSuccess) e = dalloc((void**)&h->tot, sizeof(double) * (size_t)T * TOT);
     if (e == cudaSuccess) e = dalloc((void**)&h->tot_partial, sizeof(double) * (size_t)T * h->NS * TOT);
@@ -437,7 +438,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.n = n; P.T = T; P.nloc = nloc; P.world = world; P.rank = rank; P.panel = panel; P.mode = cfg->mode;
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
-    P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
+    P.Craw = h->Craw; P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
     P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.nparts = h->nparts; P.cursor = h->cursor; P.npeers = 0;
     for (int k = 0; k < 7; ++k) P.hand_peer[k] = nullptr;
     CK(cudaDeviceSynchronize());      // the zeroed hand-over slots must be in place before any peer can write into them
@@ -456,7 +457,7 @@ int tame_destroy(tame_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int k = 0; k < h->npeers; ++k) if (h->peer_base[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
-    for (void* p : {(void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
+    for (void* p : {(void*)h->Craw, (void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
                     (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->sym_flag, (void*)h->cursor})
         if (p) cudaFree(p);
@@ -582,6 +583,7 @@ int tame_sweep(tame_handle* h) {
             }
         }
     }
+    ops->covblend(h->P, st);   // factorisation rule + damped write of the covariance blocks (chain -> Craw -> X_cov)
     ev_mark(h, 4);   // end of the sweep; folded at the next synchronisation (tame_elbo_mse)
     CK(cudaGetLastError());
     return TAME_OK;

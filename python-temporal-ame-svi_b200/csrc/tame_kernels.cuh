@@ -23,14 +23,15 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <type_traits>
 
 #define TAME_WIN 64          // node block of the stand-alone chain launches (multi-GPU path)
 #define TAME_RING 128        // ring of new partner vectors kept per time-step warp (>= the widest inline window)
 #define TAME_CHAIN_WPC 4     // warps (time steps) per chain CTA: one per SM sub-partition, no issue/FP64 contention
-#define TAME_SPIN_LIMIT (1 << 24)
+#define TAME_SPIN_LIMIT (1 << 24)   // streaming workers' poll bound (the chain's waits are time-bounded, TAME_WATCHDOG_NS)
 #define TAME_SB 32           // sub-block of the fused sweep: rows per streaming unit, push granularity
 #define TAME_MAX_PARTS 4     // column parts per streaming unit (k_sweep): 1..TAME_MAX_PARTS
-#define TAME_REFRESH 32      // the chain re-inverts the precision from scratch every TAME_REFRESH nodes (rank-2 updates between)
+#define TAME_REFRESH 64      // the chain re-inverts the precision from scratch every TAME_REFRESH nodes (rank-2 updates between)
 
 struct TameParams {
     int n, T, nloc, world, rank, panel, mode;
@@ -38,6 +39,7 @@ struct TameParams {
     const double* Y;          // local rows
     double* Xm;
     double* Xc;
+    double* Craw;             // (nloc, T, D, D) raw covariance of the sweep (chain) -> k_covblend applies the rule + damping into Xc
     double* H;
     double* hab;
     double* tot;
@@ -418,530 +420,671 @@ __device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rowb
     return logdet;
 }
 
-// per-warp shared memory of the chain kernel
+// ------------------------------------------------------------------------------------------------------
+// The Gauss-Seidel chain (structured_mf.py:211-287, naive_mf.py:193-282).
+//
+// Warp pair <-> time step t: a CHAIN warp and a HELPER warp walk the nodes in order.  For cell (i,t)
+//   P_i = const_t + sum_{j != i} G(z_j),  G(z) = J_z' R^-1 J_z (rank 2),  z_j = [V_j, U_j] at time t (new for j<i, old for j>i)
+//   C_i = P_i^-1 (then mask / symmetrise / jitter, :270-277),  mu = C_i h_i,  damped write (:282-287).
+// The only loop-carried work is the inverse: P_{i+1} = P_i - G(z_{i+1}^old) + G(z_i^new).  The chain warp carries the raw
+// inverse in registers (lane c <-> column c) and applies the two rank-2 Woodbury corrections per node (2x2 capacitance
+// matrix, one reciprocal each); the DOWN-date with node i+1's old mean does not depend on node i's result, so it is issued
+// in the same instruction stream as node i's mean (mu = C_i h_i) and overlaps it.  Every TAME_REFRESH nodes (and at the
+// first node after foreign nodes) the inverse is rebuilt from the running moment totals by an in-place Gauss-Jordan.
+// Everything else is the helper's: ALL global loads TAME_LA nodes ahead (cp.async staging: the inline window's Y entries,
+// old means, the static partner part H, the hand-over slot of (i,t-1)), the inline window's partner sum, the AR(1) terms
+// with the NEW mean of (i,t-1) and the OLD mean of (i,t+1), the running totals, and -- multi-GPU -- the nodes of other ranks.
+// The chain warp stores its raw covariance column straight to the global scratch Craw; the factorisation rule, the
+// symmetrisation, the jitter and the damped write into X_cov happen in a streaming post-pass (k_covblend).
+// Mailboxes (shared memory):  helper -> chain  inp[k] {h without the last TAME_NL partners, old mean, those partners'
+// weights, diag(P)} + the precision column at refresh nodes (pcol);  chain -> helper  ring[k] (new z).
+// Counters h_ready / c_done.
+// ------------------------------------------------------------------------------------------------------
+#define TAME_NL 2            // trailing partners (i-NL..i-1) whose terms the chain warp adds itself: the helper runs NL nodes ahead
+#define TAME_LA 4            // look-ahead of the helper's global loads, in nodes
+#define TAME_NSLOT 8         // depth of the staging ring (power of two, >= TAME_LA + 2)
+#define TAME_NINP 4          // depth of the helper -> chain mailbox (power of two, >= TAME_NL + 2)
+#define TAME_WMAX 96         // widest inline window (partners)
+#define TAME_WATCHDOG_NS 4000000000ull
+
 template <int R>
-struct TameChainSmem {
-    static constexpr int D = 2 + 2 * R, NV = 2 * R, MP = NV + 2, TOT = TameTot<R>::TOT, DP = D + 1;
-    double ring[TAME_RING][MP];  // z = [V,U] of the last TAME_RING updated nodes at this warp's time step
+struct __align__(16) TameChainSmem {
+    static constexpr int D = 2 + 2 * R, NV = 2 * R, TOT = TameTot<R>::TOT, DP = D + 1;
+    struct Stage {                                  // one node's global inputs (cp.async destinations, 16-byte aligned)
+        double2 ywin[TAME_WMAX];                    // Y[i, wlo + s, t, :] of the inline window
+        double2 hand[D];                            // hand-over slot {new mean, tag} of (i, t-1); foreign nodes: of (i, t)
+        double mold[D], mnext[D];                   // old means of (i,t) and (i,t+1)
+        double H[TAME_MAX_PARTS][NV];               // static partner part (per column part)
+        double hab[2];
+    };
+    struct Inp {                                    // helper -> chain
+        double hrest[D];                            // h of the cell without the trailing partners' terms
+        double mold[D];
+        double wl[TAME_NL][2];                      // (w0, w1) of the trailing partners: wl[q] <-> partner i-1-q
+        double pdiag[D];                            // diag(P) without the trailing partners (naive rule)
+    };
+    double ring[TAME_RING][NV];                     // z = [V,U] (new) of the last TAME_RING nodes at this time step
+    Stage st[TAME_NSLOT];
+    double pcol[D * DP];                            // helper -> chain at refresh nodes: the precision without the trailing partners
+    Inp inp[TAME_NINP];
+    double2 wbuf[TAME_WMAX];                        // (w0, w1) of the window
+    double2 Fs[2][32];                              // F = M J' of the up-date / down-date, one row per lane
     double rowb[TAME_GJ_ROWB(D)];
-    double Cm[D * DP];
-    double Cf[D * D];
-    double cstc[D * 32];         // constant part of the precision: cstc[k*32 + lane] = column `lane`, row k
-    double cold[2][D * D + 2];   // old covariance of the current / next node (cp.async double buffer)
-    double wbuf[TAME_RING * 2];
-    double mold[D], mnew[D], mprev[D], mnext[D], hvec[D], hin[NV];
-    // inputs of node k prepared by the helper warp (double-buffered by node parity)
-    struct Inp { double hin[NV]; double mold[D]; double mnext[D]; double hb[D]; double wlast[2]; };
-    Inp inp[2];
-    int h_ready;                 // last node whose inputs the helper has published
-    int c_done;                  // last node the chain warp has finished (its new z is in the ring)
-    int pad_[2];                 // keep sizeof a multiple of 16 (cp.async destinations of the next warp's block)
+    double hvec[D], mprev[D], hin[NV];
+    int h_ready;                                    // last node whose inputs the helper has published
+    int c_done;                                     // last node the chain warp has finished
+    int pad_[2];
 };
 static_assert(sizeof(TameChainSmem<1>) % 16 == 0 && sizeof(TameChainSmem<2>) % 16 == 0 && sizeof(TameChainSmem<3>) % 16 == 0 &&
               sizeof(TameChainSmem<4>) % 16 == 0 && sizeof(TameChainSmem<8>) % 16 == 0, "per-warp chain block must stay 16-byte aligned");
+static_assert(TAME_LA + 2 <= TAME_NSLOT && TAME_NL + 2 <= TAME_NINP, "mailbox depth");
 
-// z component x of a mean vector held in shared memory
-template <int R>
-__device__ __forceinline__ double tame_zof(const double* m, int x) { return m[tame_zidx<R>(x)]; }
+// time-bounded spinning: every 1024 failed polls look at the abort flag and at the clock
+struct TameSpin {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    // the slow check: abort raised by anyone, or this wait older than the watchdog (which then raises it)
+    __device__ __forceinline__ bool check(int* abort_flag) {
+        if (*((volatile int*)abort_flag)) return true;
+        const unsigned long long now = tame_globaltimer();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > TAME_WATCHDOG_NS) { atomicExch(abort_flag, 1); return true; }
+        return false;
+    }
+    __device__ __forceinline__ bool expired(int* abort_flag) { return ((++spins & 1023u) == 0) && check(abort_flag); }
+};
 
-// bounded spin on a shared-memory counter written by the partner warp of the same CTA
-__device__ __forceinline__ void tame_wait_smem(const int* flag, int target, int lane, int* abort_flag) {
-    if (lane == 0) {
-        int spins = 0;
-        while (*((volatile const int*)flag) < target) {
-            if (++spins > TAME_SPIN_LIMIT) { atomicExch(abort_flag, 1); break; }
-            if ((spins & 1023) == 0 && *((volatile int*)abort_flag)) break;
+// wait until a shared-memory counter written by the partner warp reaches `target`; false = abort.  Every lane polls the same
+// word (one broadcast LDS per poll), so the branch is warp-uniform and the ready case costs one load.
+__device__ __forceinline__ bool tame_wait_smem(const int* flag, int target, int lane, int* abort_flag) {
+    if (*((volatile const int*)flag) < target) {
+        TameSpin sp;
+        for (;;) {
+            if (*((volatile const int*)flag) >= target) break;
+            if ((++sp.spins & 1023u) == 0) {
+                const int ex = (lane == 0 && sp.check(abort_flag)) ? 1 : 0;
+                if (__any_sync(0xffffffffu, ex)) return false;
+            }
         }
     }
     __syncwarp();
-    __threadfence_block();
+    return true;
 }
 
-// Helper warp of time step t (warps 4..7 of a chain CTA): everything of node k that does not sit on the chain's critical
-// path -- the strided loads of the inline window's Y entries, the window's partial sum over the ring (all partners
-// up to k-2; the chain adds partner k-1 itself), the node's old means, the stamp of its streaming unit and the static
-// partner part H -- prepared one to two nodes ahead and handed over through double-buffered shared memory.
+// F = M J_z' for the symmetric matrix whose column (= row) c is cw[]:  f0 = (M g0)[c], f1 = (M g1)[c],
+// g0 = (1,0,V,0), g1 = (0,1,0,U), z = [V,U]
+template <int R>
+__device__ __forceinline__ void tame_rank2_F(const double (&cw)[2 + 2 * R], const double (&z)[2 * R], double& f0, double& f1) {
+    double a0 = cw[0], a1 = 0.0, b0 = cw[1], b1 = 0.0;
+#pragma unroll
+    for (int x = 0; x < R; ++x) {
+        if (x & 1) a1 = fma(cw[2 + x], z[x], a1); else a0 = fma(cw[2 + x], z[x], a0);
+        if (x & 1) b1 = fma(cw[2 + R + x], z[R + x], b1); else b0 = fma(cw[2 + R + x], z[R + x], b0);
+    }
+    f0 = a0 + a1;
+    f1 = b0 + b1;
+}
+// cw <- (M + sigma J_z' R^-1 J_z)^-1 = M^-1... in inverse form: cw - F (sigma R + J_z F)^-1 F'   (Woodbury; Rxx = (R^-1)^-1)
+template <int R>
+__device__ __forceinline__ void tame_rank2_apply(double (&cw)[2 + 2 * R], const double (&z)[2 * R], double f0, double f1,
+                                                 const double2* Fs, double sigma, double R00, double R01, double R11) {
+    constexpr int D = 2 + 2 * R;
+    double2 F[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) F[k] = Fs[k];
+    double K00 = fma(sigma, R00, F[0].x), K01 = fma(sigma, R01, F[0].y), K11 = fma(sigma, R11, F[1].y);
+    double a1 = 0.0, b1 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int x = 0; x < R; ++x) {
+        if (x & 1) { a1 = fma(z[x], F[2 + x].x, a1); b1 = fma(z[x], F[2 + x].y, b1); c1 = fma(z[R + x], F[2 + R + x].y, c1); }
+        else { K00 = fma(z[x], F[2 + x].x, K00); K01 = fma(z[x], F[2 + x].y, K01); K11 = fma(z[R + x], F[2 + R + x].y, K11); }
+    }
+    K00 += a1; K01 += b1; K11 += c1;
+    const double rd = tame_rcp(fma(K00, K11, -K01 * K01));
+    const double v0 = fma(K11, f0, -K01 * f1) * rd, v1 = fma(K00, f1, -K01 * f0) * rd;
+#pragma unroll
+    for (int k = 0; k < D; ++k) cw[k] = fma(-F[k].x, v0, fma(-F[k].y, v1, cw[k]));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// helper warp of time step t
+// ------------------------------------------------------------------------------------------------------
 template <int R, bool FUSED>
 __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChainSmem<R>& sm, int lane, int t, int i0, int i1) {
     using S = TameChainSmem<R>;
-    constexpr int WSB = FUSED ? TAME_SB : TAME_WIN, WBACK = FUSED ? 2 : 0;
-    constexpr int D = S::D, NV = S::NV, NWS = FUSED ? 3 : 2;
-    const int T = P.T, c = lane;
-    const bool has_next = t < T - 1;
-    const int nslices = (T + 31) / 32;
-    for (int k = i0; k < i1; ++k) {
-        if (FUSED && P.npeers > 0 && !tame_owned(k, P.panel, P.world, P.rank)) continue;   // the chain follows foreign nodes itself
-        const int l = tame_lrow(k, P.panel, P.world);
-        const int wlo = max(0, (k / WSB - WBACK) * WSB), cnt = k - wlo;
-        // loads that do not depend on the chain
-        double2 yv[NWS];
-#pragma unroll
-        for (int s = 0; s < NWS; ++s) {
-            const int j = wlo + lane + 32 * s;
-            yv[s] = (j < k) ? tame_ld_stream2(P.Y + (((size_t)l * P.n + j) * T + t) * 2) : make_double2(0.0, 0.0);
-        }
-        double mo = 0.0, mn = 0.0;
-        if (c < D) {
-            mo = tame_ld_cg(P.Xm + ((size_t)k * T + t) * D + c);
-            mn = has_next ? tame_ld_cg(P.Xm + ((size_t)k * T + t + 1) * D + c) : 0.0;
-        }
-        if (FUSED && (k % TAME_SB) == 0) {
-            // the static partner part H of this sub-block comes from streaming CTAs of the same launch
-            if (lane == 0) {
-                const int* flag = P.unit_done + ((l / TAME_SB) * nslices + (t >> 5)) * P.nparts;
-                int spins = 0;
-                for (int part = 0; part < P.nparts; ++part) {
-                    while (tame_ld_acquire(flag + part) != P.epoch) {
-                        if (++spins > TAME_SPIN_LIMIT) { atomicExch(P.abort_flag, 1); break; }
-                        if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        double hb = 0.0;
-        if (c < 2) hb = P.hab[((size_t)l * T + t) * 2 + c];
-        else if (c < D) {
-            const size_t slab = (size_t)P.nloc * T * NV;
-            const double* hp = P.H + ((size_t)l * T + t) * NV + (c - 2);
-            double part[TAME_MAX_PARTS];
-#pragma unroll
-            for (int pp = 0; pp < TAME_MAX_PARTS; ++pp) part[pp] = (pp < (FUSED ? P.nparts : 1)) ? __ldcg(hp + pp * slab) : 0.0;
-            hb = (part[0] + part[1]) + (part[2] + part[3]);
-        }
-        // the window's weights
-#pragma unroll
-        for (int s = 0; s < NWS; ++s) {
-            const int slot = lane + 32 * s;
-            sm.wbuf[slot * 2 + 0] = P.p0 * yv[s].x + P.q * yv[s].y;
-            sm.wbuf[slot * 2 + 1] = P.q * yv[s].x + P.p1 * yv[s].y;
-        }
-        // the ring must hold every node up to k-2, and the chain must be done with this input buffer (node k-2)
-        if (k - 2 >= i0) tame_wait_smem(&sm.c_done, k - 2, lane, P.abort_flag);
-        else __syncwarp();
-        // partial window sum over the partners wlo .. k-2  (slots 0 .. cnt-2)
-        const int cnt1 = max(cnt - 1, 0);
-        const int x = lane & 15, half = lane >> 4;
-        double acc = 0.0;
-        {
-            const int xx = min(x, NV - 1), wsel = (xx < R) ? 0 : 1;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int jj = half;
-            for (; jj + 6 < cnt1; jj += 8) {
-                a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
-                a1 = fma(sm.wbuf[(jj + 2) * 2 + wsel], sm.ring[(wlo + jj + 2) & (TAME_RING - 1)][xx], a1);
-                a2 = fma(sm.wbuf[(jj + 4) * 2 + wsel], sm.ring[(wlo + jj + 4) & (TAME_RING - 1)][xx], a2);
-                a3 = fma(sm.wbuf[(jj + 6) * 2 + wsel], sm.ring[(wlo + jj + 6) & (TAME_RING - 1)][xx], a3);
-            }
-            for (; jj < cnt1; jj += 2) a0 = fma(sm.wbuf[jj * 2 + wsel], sm.ring[(wlo + jj) & (TAME_RING - 1)][xx], a0);
-            acc = (x < NV) ? (a0 + a1) + (a2 + a3) : 0.0;
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        typename S::Inp& in = sm.inp[k & 1];
-        if (lane < NV) in.hin[lane] = acc;
-        if (c < D) { in.mold[c] = mo; in.mnext[c] = mn; in.hb[c] = hb; }
-        if (lane < 2) in.wlast[lane] = (cnt >= 1) ? sm.wbuf[(cnt - 1) * 2 + lane] : 0.0;
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) *((volatile int*)&sm.h_ready) = k;
-    }
-}
+    constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP;
+    constexpr int WSB = FUSED ? TAME_SB : TAME_WIN, WBACK = FUSED ? 2 : 0, NWS = FUSED ? 3 : 2;
+    constexpr int NL = TAME_NL, LA = TAME_LA, SMASK = TAME_NSLOT - 1, IMASK = TAME_NINP - 1, RMASK = TAME_RING - 1;
+    const int T = P.T, c = lane, cc = min(c, D - 1);
+    const bool act = c < D, has_prev = t > 0, has_next = t < T - 1;
+    const bool multi = FUSED && P.npeers > 0;
+    const int nslices = (T + 31) / 32, nparts = FUSED ? P.nparts : 1;
+    const double m1 = (double)(P.n - 1);
+    const unsigned long long magic = 0x5AFE000000000000ull + (unsigned long long)(unsigned)P.epoch;
+    const size_t slab = (size_t)P.nloc * T * NV;
+    const double2* hand_prev = P.hand + (size_t)max(t - 1, 0) * D + cc;     // + i*T*D : slot of (i, t-1), component cc
+    const double2* hand_mine = P.hand + (size_t)t * D + cc;
+    auto owned = [&](int k) { return !multi || tame_owned(k, P.panel, P.world, P.rank); };
+    auto lrow = [&](int k) { return (P.world == 1) ? k : tame_lrow(k, P.panel, P.world); };
+    auto window_lo = [&](int k) { return max(i0, (k / WSB - WBACK) * WSB); };
+    auto tag_ok = [&](const double2& v) {
+        return ((unsigned long long)__double_as_longlong(v.x) ^ (unsigned long long)__double_as_longlong(v.y)) == magic;
+    };
 
-// ------------------------------------------------------------------------------------------------------
-// k_chain: the Gauss-Seidel chain over nodes [i0,i1) (one panel, i1-i0 <= TAME_WIN, owned by this rank).
-// Warp <-> time step t.  For each node in order the warp
-//   1. removes the node's own term from the running totals, builds P = P_obs + prior/AR precision
-//      (structured_mf.py:246-264) and inverts it (:267),
-//   2. applies the factorisation mask / symmetrisation / jitter (:270-277) or the naive rule (naive_mf.py:268-274),
-//   3. assembles h: static partner part H + inline window (partners of this panel already updated) + AR terms
-//      with the NEW mean of (i,t-1) handed over by warp t-1 and the OLD mean of (i,t+1),
-//   4. writes the damped mean/covariance (:282-287), publishes progress, restores the totals with the new mean.
-// Launched cooperatively (all CTAs co-resident): warps spin on their predecessor's progress counter.
-// ------------------------------------------------------------------------------------------------------
-template <int R, bool FUSED>
-__device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned char* smem_raw, int cta, int i0, int i1) {
-    using S = TameChainSmem<R>;
-    // inline window: FUSED  -> the two previous + the current 32-node sub-block (the streaming CTAs cover everything
-    //                          older; two sub-blocks of slack absorb the ~1 node/time-step stagger of the warps),
-    //                !FUSED -> the current 64-node block only (earlier blocks were pushed by k_contract launches)
-    constexpr int WSB = FUSED ? TAME_SB : TAME_WIN;
-    constexpr int WBACK = FUSED ? 2 : 0;
-    constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP, NE = (D * D + 31) / 32;
-    double* cstQP = reinterpret_cast<double*>(smem_raw);          // QinvPhi   (D*D)
-    double* cstPQ = cstQP + D * D;                                // Phi'Qinv  (D*D)
-    S* warps = reinterpret_cast<S*>(cstPQ + D * D);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 2 * D * D; e += blockDim.x) {      // stored transposed: [k][row], conflict-free per k
-        const int m = e / (D * D), rc = e % (D * D);
-        cstQP[m * D * D + (rc % D) * D + rc / D] = P.cst[3 * D * D + e];
-    }
-    if (threadIdx.x < TAME_CHAIN_WPC) { warps[threadIdx.x].h_ready = i0 - 1; warps[threadIdx.x].c_done = i0 - 1; }
-    __syncthreads();
-    // a chain CTA carries 8 warps: warps 0..3 are the chain warps of 4 consecutive time steps (one per SM sub-partition),
-    // warps 4..7 their helpers
-    const bool is_helper = warp >= TAME_CHAIN_WPC;
-    const int wpair = warp - (is_helper ? TAME_CHAIN_WPC : 0);
-    if (wpair >= TAME_CHAIN_WPC) return;
-    const int t = cta * TAME_CHAIN_WPC + wpair;
-    if (t >= P.T) return;
-    S& sm = warps[wpair];
-    if (is_helper) {
-        tame_chain_helper<R, FUSED>(P, sm, lane, t, i0, i1);
-        return;
-    }
-    const int T = P.T;
-    const bool has_prev = t > 0, has_next = t < T - 1;
-    const int c = lane;   // column / component owned by this lane
-
-    // constant part of the precision, column c:  (t==0 ? S0inv : Qinv) + (t<T-1 ? Phi'QinvPhi : 0)
+    // rows cc of Qinv Phi and Phi' Qinv (AR(1) terms of h, structured_mf.py:258,264) and the constant part of diag(P)
+    double qp[D], pq[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        double v = 0.0;
-        if (c < D) {
-            v = has_prev ? P.cst[1 * D * D + k * D + c] : P.cst[0 * D * D + k * D + c];
-            if (has_next) v += P.cst[2 * D * D + k * D + c];
-        }
-        sm.cstc[k * 32 + lane] = v;
+        qp[k] = P.cst[3 * D * D + cc * D + k];
+        pq[k] = P.cst[4 * D * D + cc * D + k];
     }
-    // running partner moments of this time step, held in registers: lane c >= 2 owns column y = c-2 of
-    // G = sum_j z_j z_j' (and g[y]); lanes 0,1 hold g = sum_j z_j  (z_j = [V_j, U_j]) -- exactly what the lane needs
-    // to form its column of the observation precision.
-    double Gc[NV], gy = 0.0;
+    const double cdiag = (has_prev ? P.cst[1 * D * D + cc * D + cc] : P.cst[cc * D + cc]) + (has_next ? P.cst[2 * D * D + cc * D + cc] : 0.0);
+    // running partner moments of this time step: lane c >= 2 owns column y = c-2 of G = sum_j z_j z_j' (and g[y], G[y][y]);
+    // lanes 0,1 hold g = sum_j z_j -- exactly what the lane needs to form its column of the observation precision
+    double Gc[NV], gy = 0.0, gd = 0.0;
 #pragma unroll
     for (int x = 0; x < NV; ++x) {
         double v = 0.0;
         if (c < 2) v = P.tot[(size_t)t * TOT + x];
-        else if (c < D) v = P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)];
+        else if (act) v = P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)];
         Gc[x] = v;
     }
-    if (c >= 2 && c < D) gy = P.tot[(size_t)t * TOT + (c - 2)];
-    // tot += sign * (z, z z') for the mean vector m (shared memory)
-    auto tot_update = [&](const double* m, double sign) {
-        const double zy = (c < 2) ? sign : ((c < D) ? sign * m[tame_zidx<R>(c - 2)] : 0.0);
+    if (c >= 2 && act) {
+        gy = P.tot[(size_t)t * TOT + (c - 2)];
+        gd = P.tot[(size_t)t * TOT + NV + (c - 2) * NV + (c - 2)];
+    }
+    // tot += sign * (z, z z'); z read from shared memory in z order (ring row) or from a mean vector in x order
+    using TrueT = std::true_type;
+    using FalseT = std::false_type;
+    auto tot_update = [&](const double* m, auto xorder, double sign) {
+        constexpr bool XO = decltype(xorder)::value;
+        double zy = 0.0;
+        if (c < 2) zy = sign;
+        else if (act) zy = sign * m[XO ? tame_zidx<R>(c - 2) : c - 2];
 #pragma unroll
-        for (int x = 0; x < NV; ++x) Gc[x] = fma(m[tame_zidx<R>(x)], zy, Gc[x]);
-        if (c >= 2) gy += zy;
+        for (int x = 0; x < NV; ++x) Gc[x] = fma(m[XO ? tame_zidx<R>(x) : x], zy, Gc[x]);
+        if (c >= 2) { gy += zy; gd = fma(zy * zy, sign, gd); }
     };
-    // raw inverse of the current precision, column c, carried from node to node
-    double cw[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) cw[k] = 0.0;
-    bool have_cw = false;
-    const double rdetR = 1.0 / (P.p0 * P.p1 - P.q * P.q);
-    const double R00 = P.p1 * rdetR, R11 = P.p0 * rdetR, R01 = -P.q * rdetR;      // R = (R^-1)^-1
-    // cw <- (P + sigma * J_z' R^-1 J_z)^-1 = cw - F (sigma R + J_z cw J_z')^-1 F',  F = cw J_z'  (z from the mean vector m)
-    auto rank2 = [&](const double* m, double sigma) {
-        double* Fs = sm.rowb;                                   // (D+14) x 2 scratch: F of every column
-        double f0 = cw[0], f1 = cw[1];
-#pragma unroll
-        for (int x = 0; x < R; ++x) f0 = fma(cw[2 + x], m[tame_zidx<R>(x)], f0);          // row c of C times g0 = (1,0,V,0)
-#pragma unroll
-        for (int x = R; x < NV; ++x) f1 = fma(cw[2 + x], m[tame_zidx<R>(x)], f1);         // row c of C times g1 = (0,1,0,U)
-        Fs[2 * lane] = f0;
-        Fs[2 * lane + 1] = f1;
-        __syncwarp();
-        double K00 = fma(sigma, R00, Fs[0]), K01 = fma(sigma, R01, Fs[1]), K11 = fma(sigma, R11, Fs[3]);
-#pragma unroll
-        for (int x = 0; x < R; ++x) {
-            const double zx = m[tame_zidx<R>(x)];
-            K00 = fma(zx, Fs[2 * (2 + x)], K00);
-            K01 = fma(zx, Fs[2 * (2 + x) + 1], K01);
-        }
-#pragma unroll
-        for (int x = R; x < NV; ++x) K11 = fma(m[tame_zidx<R>(x)], Fs[2 * (2 + x) + 1], K11);
-        const double rd = tame_rcp(K00 * K11 - K01 * K01);
-        const double v0 = (K11 * f0 - K01 * f1) * rd, v1 = (K00 * f1 - K01 * f0) * rd;
-#pragma unroll
-        for (int k = 0; k < D; ++k) cw[k] = fma(-Fs[2 * k], v0, fma(-Fs[2 * k + 1], v1, cw[k]));
-        __syncwarp();
-    };
-    // scale pattern of P_obs (see header): rows x<R of the z-block use sA, rows x>=R use sB
-    double sA, sB;
+    double sA, sB;   // scale pattern of P_obs: rows x<R of the z-block use sA, rows x>=R use sB
     if (c == 0) { sA = P.p0; sB = P.q; }
     else if (c == 1) { sA = P.q; sB = P.p1; }
     else if (c - 2 < R) { sA = P.p0; sB = P.q; }
     else { sA = P.q; sB = P.p1; }
-    const double m1 = (double)(P.n - 1);
-    const double lr = P.lr, om = 1.0 - P.lr;
-    __syncwarp();
 
-    const unsigned long long magic = 0x5AFE000000000000ull + (unsigned long long)(unsigned)P.epoch;
-    const double2* hand_prev = P.hand + (size_t)(t - 1) * D + min(c, D - 1);   // + i*T*D : slot of (i, t-1), lane c
-    double2* hand_mine = P.hand + (size_t)t * D + min(c, D - 1);
-    auto window_lo = [&](int i) { return max(0, (i / WSB - WBACK) * WSB); };
+    long long wait_unit = 0, wait_hand = 0, wait_chain = 0;
+    bool alive = true;
 
-    // old covariance of node i -> shared (asynchronous 16-byte copies; X_cov blocks are 16-byte aligned); everything else
-    // of the node's inputs comes from the helper warp
-    auto prefetch = [&](int i) {
-        const double* cp = P.Xc + ((size_t)i * T + t) * D * D;
-        double* dst = sm.cold[i & 1];
-        for (int e = lane; e < (D * D) / 2; e += 32) tame_cp_async16(dst + 2 * e, cp + 2 * e, true);
-        tame_cp_async_commit();
-    };
-    prefetch(i0);
-    const bool probe = FUSED && lane == 0 && (t == 0 || t == T - 1);     // timing probes (dbg[0..7]: t=0, [8..15]: t=T-1)
-    unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
-    long long wait_unit = 0, wait_hand = 0, t_gj = 0;
-    if (probe) dbg[0] = tame_globaltimer();
-
-    bool prefetched = true;           // the registers/ring slots of node i were loaded by prefetch(i)
-    for (int i = i0; i < i1; ++i) {
-        if (FUSED && P.npeers > 0 && !tame_owned(i, P.panel, P.world, P.rank)) {
-            // ---- multi-GPU follower: node i belongs to another rank.  Its owner wrote {new mean, tag} straight into this
-            // rank's hand-over slots over NVLink; take it, keep the running moments, the window ring and the replicated
-            // X_mean in step, skip everything else (no inverse, no covariance).
-            double mo_f = 0.0;
-            if (c < D) mo_f = tame_ld_cg(P.Xm + ((size_t)i * T + t) * D + c);
-            double2 hf = make_double2(0.0, 0.0);
-            int spins = 0;
-            for (;;) {
-                if (c < D) hf = tame_ld_volatile2(hand_mine + (size_t)i * T * D);
-                const bool ok = (c >= D) ||
-                    (((unsigned long long)__double_as_longlong(hf.x) ^ (unsigned long long)__double_as_longlong(hf.y)) == magic);
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (++spins > TAME_SPIN_LIMIT) { if (lane == 0) atomicExch(P.abort_flag, 1); break; }
-                if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
+    // stage ALL global inputs of node k (cp.async; the caller commits one group per loop iteration).  At the first node of a
+    // sub-block the stamp of its streaming unit (static partner part H) is awaited first.
+    auto stage = [&](int k) {
+        typename S::Stage& s = sm.st[k & SMASK];
+        const size_t cell = (size_t)k * T + t;
+        const double* xm = P.Xm + cell * D;
+        if (lane < D / 2) tame_cp_async16(&s.mold[2 * lane], xm + 2 * lane, true);
+        if (!owned(k)) {
+            if (act) tame_cp_async16(&s.hand[c], hand_mine + (size_t)k * T * D, true);
+            return;
+        }
+        if (has_prev && act) tame_cp_async16(&s.hand[c], hand_prev + (size_t)k * T * D, true);
+        if (has_next && lane >= 16 && lane < 16 + D / 2) tame_cp_async16(&s.mnext[2 * (lane - 16)], xm + D + 2 * (lane - 16), true);
+        const int l = lrow(k), wlo = window_lo(k);
+        const double* yb = P.Y + (((size_t)l * P.n + wlo) * T + t) * 2;
+#pragma unroll
+        for (int u = 0; u < NWS; ++u) {
+            const int sl = lane + 32 * u;
+            if (wlo + sl < k) tame_cp_async16(&s.ywin[sl], yb + (size_t)sl * T * 2, true);
+        }
+        if (FUSED && (k % TAME_SB) == 0) {
+            const long long c0 = clock64();
+            int ok = 1;
+            if (lane == 0) {
+                const int* flag = P.unit_done + ((l / TAME_SB) * nslices + (t >> 5)) * P.nparts;
+                TameSpin sp;
+                for (int part = 0; part < P.nparts && ok; ++part)
+                    while (tame_ld_acquire(flag + part) != P.epoch)
+                        if (sp.expired(P.abort_flag)) { ok = 0; break; }
             }
-            if (c < D) {
-                sm.mold[c] = mo_f;
-                sm.mnew[c] = hf.x;
-                tame_st_cg(P.Xm + ((size_t)i * T + t) * D + c, hf.x);
-            }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
             __syncwarp();
-            tot_update(sm.mold, -1.0);
-            tot_update(sm.mnew, 1.0);
-            if (lane < NV) sm.ring[i & (TAME_RING - 1)][lane] = tame_zof<R>(sm.mnew, lane);
-            if (((i + 1) % TAME_SB) == 0 || i + 1 == i1) {
+            wait_unit += clock64() - c0;
+            if (!ok) { alive = false; return; }
+        }
+        const size_t lcell = (size_t)l * T + t;
+        if (lane == 31) tame_cp_async16(&s.hab[0], P.hab + lcell * 2, true);
+        if (lane < nparts * R) {
+            const int part = lane / R, piece = lane - part * R;
+            tame_cp_async16(&s.H[part][2 * piece], P.H + part * slab + lcell * NV + 2 * piece, true);
+        }
+    };
+
+    for (int u = 0; u <= LA; ++u) {
+        if (alive && i0 + u < i1) stage(i0 + u);
+        tame_cp_async_commit();
+    }
+    for (int k = i0; k < i1 && alive; ++k) {
+        const bool mine = owned(k);
+        tame_cp_async_wait<LA>();
+        __syncwarp();
+        const typename S::Stage& s = sm.st[k & SMASK];
+
+        // ---- totals: node k-1-NL enters with its new mean (its z is in the ring), node k leaves with its old mean
+        const int jf = k - 1 - NL;
+        if (jf >= i0) {
+            if (owned(jf)) {
+                const long long c0 = clock64();
+                if (!tame_wait_smem(&sm.c_done, jf, lane, P.abort_flag)) { alive = false; break; }
+                wait_chain += clock64() - c0;
+            }
+            tot_update(sm.ring[jf & RMASK], FalseT{}, 1.0);
+        }
+        tot_update(s.mold, TrueT{}, -1.0);
+
+        if (!mine) {
+            // ---- node of another rank: its owner wrote {new mean, tag} straight into this rank's hand-over slots over
+            // NVLink; keep the replicated X_mean, the window ring and the progress counter in step
+            double2 hf = s.hand[cc];
+            TameSpin sp;
+            for (;;) {
+                if (__all_sync(0xffffffffu, !act || tag_ok(hf))) break;
+                int ex = 0;
+                if (lane == 0) ex = sp.expired(P.abort_flag) ? 1 : 0;
+                if (__shfl_sync(0xffffffffu, ex, 0)) { alive = false; break; }
+                if (act) hf = tame_ld_volatile2(hand_mine + (size_t)k * T * D);
+            }
+            if (!alive) break;
+            if (act) {
+                tame_st_cg(P.Xm + ((size_t)k * T + t) * D + c, hf.x);
+                if (c >= 2) sm.ring[k & RMASK][(c - 2 < R) ? c - 2 + R : c - 2 - R] = hf.x;
+            }
+            if (((k + 1) % TAME_SB) == 0 || k + 1 == i1) {
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) tame_st_release(P.progress + t, i + 1);
+                if (lane == 0) tame_st_release(P.progress + t, k + 1);
+            }
+        } else {
+            // ---- the window's weights  w0 = p0 y0 + q y1, w1 = q y0 + p1 y1  (structured_mf.py:324)
+            const int wlo = window_lo(k), nle = min(NL, k - i0), cnt = (k - nle) - wlo;     // helper sums partners wlo .. k-nle-1
+#pragma unroll
+            for (int u = 0; u < NWS; ++u) {
+                const int sl = lane + 32 * u;
+                if (wlo + sl < k) {
+                    const double2 y = s.ywin[sl];
+                    sm.wbuf[sl] = make_double2(P.p0 * y.x + P.q * y.y, P.q * y.x + P.p1 * y.y);
+                }
+            }
+            // ---- AR(1) term of the successor (old mean) + static partner part
+            double hval = 0.0;
+            if (c < 2) hval = s.hab[c];
+            else if (act) {
+                for (int pp = 0; pp < nparts; ++pp) hval += s.H[pp][c - 2];
+            }
+            if (has_next) {
+                double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+#pragma unroll
+                for (int q = 0; q + 2 < D; q += 3) {
+                    n0 = fma(pq[q], s.mnext[q], n0);
+                    n1 = fma(pq[q + 1], s.mnext[q + 1], n1);
+                    n2 = fma(pq[q + 2], s.mnext[q + 2], n2);
+                }
+#pragma unroll
+                for (int q = (D / 3) * 3; q < D; ++q) n0 = fma(pq[q], s.mnext[q], n0);
+                hval += (n0 + n1) + n2;                                  // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
+            }
+            // ---- (k, t-1): the staged look at its hand-over slot; poll only if the predecessor is not that far ahead
+            if (has_prev) {
+                double2 hv = s.hand[cc];
+                if (!__all_sync(0xffffffffu, !act || tag_ok(hv))) {
+                    const long long c0 = clock64();
+                    TameSpin sp;
+                    for (;;) {
+                        if (act) hv = tame_ld_volatile2(hand_prev + (size_t)k * T * D);
+                        if (__all_sync(0xffffffffu, !act || tag_ok(hv))) break;
+                        int ex = 0;
+                        if (lane == 0) ex = sp.expired(P.abort_flag) ? 1 : 0;
+                        if (__shfl_sync(0xffffffffu, ex, 0)) { alive = false; break; }
+                    }
+                    wait_hand += clock64() - c0;
+                    if (!alive) break;
+                }
+                if (act) sm.mprev[c] = hv.x;
+            }
+            __syncwarp();        // wbuf, mprev
+            // ---- partial window sum over the ring: lane = (partner phase, component pair); NPP pairs x PH phases = 32 lanes
+            {
+                constexpr int NPP = (R <= 1) ? 1 : (R <= 2) ? 2 : (R <= 4) ? 4 : 8, PH = 32 / NPP;
+                const int xp = min(lane % NPP, R - 1), ph = lane / NPP, x0 = 2 * xp;
+                const bool a0 = x0 < R, a1 = x0 + 1 < R;
+                double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
+                int jj = ph;
+                for (; jj + PH < cnt; jj += 2 * PH) {
+                    const double2 wa = sm.wbuf[jj], wb = sm.wbuf[jj + PH];
+                    const double2 za = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                    const double2 zb = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj + PH) & RMASK][x0]);
+                    s0 = fma(a0 ? wa.x : wa.y, za.x, s0);
+                    u0 = fma(a1 ? wa.x : wa.y, za.y, u0);
+                    s1 = fma(a0 ? wb.x : wb.y, zb.x, s1);
+                    u1 = fma(a1 ? wb.x : wb.y, zb.y, u1);
+                }
+                if (jj < cnt) {
+                    const double2 wa = sm.wbuf[jj];
+                    const double2 za = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                    s0 = fma(a0 ? wa.x : wa.y, za.x, s0);
+                    u0 = fma(a1 ? wa.x : wa.y, za.y, u0);
+                }
+                s0 += s1;
+                u0 += u1;
+#pragma unroll
+                for (int o = NPP; o < 32; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+                }
+                if (lane < NPP && lane < R) { sm.hin[x0] = s0; sm.hin[x0 + 1] = u0; }
+            }
+            if (has_prev) {
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+#pragma unroll
+                for (int q = 0; q + 2 < D; q += 3) {
+                    p0 = fma(qp[q], sm.mprev[q], p0);
+                    p1 = fma(qp[q + 1], sm.mprev[q + 1], p1);
+                    p2 = fma(qp[q + 2], sm.mprev[q + 2], p2);
+                }
+#pragma unroll
+                for (int q = (D / 3) * 3; q < D; ++q) p0 = fma(qp[q], sm.mprev[q], p0);
+                hval += (p0 + p1) + p2;                                  // Qinv Phi mu_{t-1}      (structured_mf.py:258)
+            }
+            __syncwarp();        // hin
+            if (c >= 2 && act) hval += sm.hin[c - 2];
+            // ---- publish node k's inputs
+            typename S::Inp& in = sm.inp[k & IMASK];
+            if (act) {
+                in.hrest[c] = hval;
+                in.mold[c] = s.mold[c];
+                in.pdiag[c] = cdiag + ((c < 2) ? ((c == 0) ? P.p0 : P.p1) * m1 : ((c - 2 < R) ? P.p0 : P.p1) * gd);
+            }
+            if (lane < 2 * nle) {               // wl[q] <-> partner k-1-q
+                const int q = lane >> 1;
+                const double2 w = sm.wbuf[cnt + nle - 1 - q];
+                in.wl[q][lane & 1] = (lane & 1) ? w.y : w.x;
+            }
+            if (k == i0 || (k % TAME_REFRESH) == 0) {
+                // precision column c without the trailing partners (the chain adds them and inverts)
+                if (act) {
+                    const size_t cb = (size_t)(has_prev ? 1 : 0) * D * D;
+                    double c0v, c1v;
+                    if (c < 2) { c0v = ((c == 0) ? P.p0 : P.q) * m1; c1v = ((c == 0) ? P.q : P.p1) * m1; }
+                    else { c0v = sA * gy; c1v = sB * gy; }
+#pragma unroll
+                    for (int q = 0; q < D; ++q) {
+                        double v = (q == 0) ? c0v : (q == 1) ? c1v : ((q - 2 < R) ? sA : sB) * Gc[(q >= 2) ? q - 2 : 0];
+                        v += P.cst[cb + q * D + c];
+                        if (has_next) v += P.cst[2 * D * D + q * D + c];
+                        sm.pcol[q * DP + c] = v;
+                    }
+                }
             }
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) *((volatile int*)&sm.c_done) = i;
-            have_cw = false;          // the carried inverse is rebuilt at the next owned node
-            prefetched = false;
-            continue;
+            if (lane == 0) *((volatile int*)&sm.h_ready) = k;
         }
-        if (!prefetched) {            // first owned node after foreign ones
-            prefetch(i);
-            prefetched = true;
-        }
-        // ---- start the next node's covariance copy, then take this node's inputs from the helper warp
-        const bool next_mine = (i + 1 < i1) && !(FUSED && P.npeers > 0 && !tame_owned(i + 1, P.panel, P.world, P.rank));
-        if (next_mine) prefetch(i + 1); else prefetched = false;
+        // ---- next inputs
+        __syncwarp();
+        if (k + 1 + LA < i1) stage(k + 1 + LA);
+        tame_cp_async_commit();
+    }
+    // ---- drain: the last nodes' totals
+    tame_cp_async_wait<0>();
+    __syncwarp();
+    for (int jf = max(i0, i1 - 1 - NL); jf < i1 && alive; ++jf) {
+        if (owned(jf) && !tame_wait_smem(&sm.c_done, jf, lane, P.abort_flag)) { alive = false; break; }
+        tot_update(sm.ring[jf & RMASK], FalseT{}, 1.0);
+    }
+    if (!alive) return;            // watchdog: leave the running totals alone, the caller reports TAME_EHANG
+    if (c >= 2 && act) {
+        P.tot[(size_t)t * TOT + (c - 2)] = gy;
+#pragma unroll
+        for (int x = 0; x < NV; ++x) P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)] = Gc[x];
+    }
+    if (FUSED && lane == 0 && (t == 0 || t == T - 1)) {
+        unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
+        dbg[3] = (unsigned long long)wait_unit;
+        dbg[4] = (unsigned long long)wait_hand;
+        dbg[5] = (unsigned long long)wait_chain;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// chain warp of time step t
+// ------------------------------------------------------------------------------------------------------
+template <int R, bool FUSED>
+__device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSmem<R>& sm, int lane, int t, int i0, int i1) {
+    using S = TameChainSmem<R>;
+    constexpr int D = S::D, NV = S::NV, DP = S::DP;
+    constexpr int NL = TAME_NL, IMASK = TAME_NINP - 1, RMASK = TAME_RING - 1;
+    const int T = P.T, c = lane, cc = min(c, D - 1);
+    const bool act = c < D, has_next = t < T - 1;
+    const bool multi = FUSED && P.npeers > 0;
+    const int mode = P.mode;
+    const double lr = P.lr, om = 1.0 - P.lr;
+    const double rdetR = 1.0 / (P.p0 * P.p1 - P.q * P.q);
+    const double R00 = P.p1 * rdetR, R11 = P.p0 * rdetR, R01 = -P.q * rdetR;      // R = (R^-1)^-1
+    const unsigned long long magic = 0x5AFE000000000000ull + (unsigned long long)(unsigned)P.epoch;
+    auto owned = [&](int k) { return !multi || tame_owned(k, P.panel, P.world, P.rank); };
+    auto refresh_at = [&](int k) { return k == i0 || (k % TAME_REFRESH) == 0; };
+    // component c of x = [a,b,U,V] sits at zpos in z = [V,U]; its h entry takes w0 (U rows) or w1 (V rows)
+    const int zc = (cc >= 2) ? cc - 2 : 0;                       // index of this lane's component in h[2:], H, hin, ring rows
+    const int zpos = (zc < R) ? zc + R : zc - R;                 // where its own new value goes in a ring row
+    const int wsel = (zc < R) ? 0 : 1;
+    const bool zlane = act && c >= 2;
+    const double sdiag = (zc < R) ? P.p0 : P.p1;
+    const bool lo = c < 2;
+
+    double cw[D];            // raw inverse, column (= row) c; after a down-date it is B_{i+1}^-1
+#pragma unroll
+    for (int k = 0; k < D; ++k) cw[k] = 0.0;
+    const bool probe = FUSED && lane == 0 && (t == 0 || t == T - 1);     // timing probes (dbg[0..7]: t=0, [8..15]: t=T-1)
+    unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
+    long long wait_in = 0;
+    int ncell = 0;
+    if (probe) dbg[0] = tame_globaltimer();
+    // running addresses of (i, t, c)
+    const size_t nstride = (size_t)T * D;
+    size_t xoff = ((size_t)i0 * T + t) * D + cc;
+
+    for (int i = i0; i < i1; ++i, xoff += nstride) {
+        if (!owned(i)) continue;
+        const bool refresh = refresh_at(i);
+        const bool do_down = (i + 1 < i1) && owned(i + 1) && !refresh_at(i + 1);
         {
             const long long c0 = clock64();
-            tame_wait_smem(&sm.h_ready, i, lane, P.abort_flag);
-            wait_unit += clock64() - c0;
+            if (!tame_wait_smem(&sm.h_ready, do_down ? i + 1 : i, lane, P.abort_flag)) return;
+            wait_in += clock64() - c0;
             if (probe && i == i0) dbg[1] = tame_globaltimer();
         }
-        // first look at the hand-over slot of (i, t-1): issued now (after the wait on the helper), checked after the inverse
-        double2 hv = make_double2(0.0, 0.0);
-        if (has_prev && c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
-        const typename S::Inp& in = sm.inp[i & 1];
-        const double mo = (c < D) ? in.mold[c] : 0.0, mn = (c < D) ? in.mnext[c] : 0.0;
-        double hb = (c < D) ? in.hb[c] : 0.0;
-        const int wlo = window_lo(i);
-
-        if (c < D) { sm.mold[c] = mo; sm.mnext[c] = mn; }
-        __syncwarp();
-        tot_update(sm.mold, -1.0);
-
-        // ---- precision column c  (needed at refresh nodes; in naive mode always, for diag(P))
-        const bool refresh = !have_cw || ((i % TAME_REFRESH) == 0);
-        double col[D];
-        double pdiag = 0.0;
-        if (refresh || P.mode == 0) {
-            if (c < 2) {
-                col[0] = (c == 0) ? P.p0 * m1 : P.q * m1;
-                col[1] = (c == 0) ? P.q * m1 : P.p1 * m1;
-            } else {
-                col[0] = sA * gy;
-                col[1] = sB * gy;
-            }
+        const typename S::Inp& in = sm.inp[i & IMASK];
+        const int nle = min(NL, i - i0);
+        const double mo = in.mold[cc];
+        // ---- h: the helper's part + the trailing partners i-1-q (new z in the ring)
+        double hval = in.hrest[cc];
+        double pdiag = in.pdiag[cc];
 #pragma unroll
-            for (int x = 0; x < NV; ++x) col[2 + x] = ((x < R) ? sA : sB) * Gc[x];
-#pragma unroll
-            for (int k = 0; k < D; ++k) col[k] += sm.cstc[k * 32 + lane];
-            if (P.mode == 0) {          // naive rule needs diag(P) (naive_mf.py:271-274)
-#pragma unroll
-                for (int k = 0; k < D; ++k) pdiag = (k == c) ? col[k] : pdiag;
+        for (int q = 0; q < NL; ++q) {
+            const double zj = sm.ring[(i - 1 - q) & RMASK][zc];
+            const double w = in.wl[q][wsel];
+            if (q < nle && zlane) {
+                hval = fma(w, zj, hval);
+                pdiag = fma(sdiag * zj, zj, pdiag);
             }
         }
+        if (act) sm.hvec[c] = hval;
 
-        // ---- inline window: the helper summed the partners wlo..i-2; partner i-1 (whose new z this warp wrote last) is added here
-        if (lane < NV) {
-            double acc = in.hin[lane];
-            if (i - wlo >= 1) acc = fma(in.wlast[(lane < R) ? 0 : 1], sm.ring[(i - 1) & (TAME_RING - 1)][lane], acc);
-            sm.hin[lane] = acc;
-        }
-
-        // ---- inverse of the precision.  P_i = P_{i-1} + G(z_{i-1}^new) - G(z_i^old) with G(z) = J_z' R^-1 J_z of rank 2, so
-        // between refreshes the carried raw inverse cw[] follows by two rank-2 (Woodbury) corrections, each with a 2x2
-        // capacitance matrix and one reciprocal; every TAME_REFRESH nodes it is recomputed from scratch (no drift).
-        const long long cg0 = clock64();
         if (refresh) {
+            // ---- precision column from the totals (helper) + the trailing partners' rank-2 terms, Gauss-Jordan
+            double col[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) col[k] = act ? sm.pcol[k * DP + c] : 0.0;
+            for (int q = 0; q < nle; ++q) {
+                const double* zr = sm.ring[(i - 1 - q) & RMASK];
+                const double zj = zr[zc];
+                const double g0c = (c == 0) ? 1.0 : ((c >= 2 && zc < R) ? zj : 0.0);      // g0 = (1,0,V,0)
+                const double g1c = (c == 1) ? 1.0 : ((c >= 2 && zc >= R) ? zj : 0.0);     // g1 = (0,1,0,U)
+                const double al = P.p0 * g0c + P.q * g1c, be = P.q * g0c + P.p1 * g1c;
+                if (act) {
+                    if (c >= 2) { col[0] += al; col[1] += be; }          // the (a,b) block already counts all n-1 partners
+#pragma unroll
+                    for (int x = 0; x < R; ++x) {
+                        col[2 + x] = fma(zr[x], al, col[2 + x]);
+                        col[2 + R + x] = fma(zr[R + x], be, col[2 + R + x]);
+                    }
+                }
+            }
             tame_gj_inverse<D, false>(col, sm.rowb, lane);
 #pragma unroll
             for (int k = 0; k < D; ++k) cw[k] = col[k];
-            have_cw = true;
+            __syncwarp();
         } else {
-            rank2(sm.mnew, 1.0);       // node i-1 re-enters with its new mean (sm.mnew still holds it)
-            rank2(sm.mold, -1.0);      // node i leaves with its old mean
+            // ---- up-date: node i-1 re-enters with its new mean
+            double z[NV];
+            const double2* zr = reinterpret_cast<const double2*>(sm.ring[(i - 1) & RMASK]);
 #pragma unroll
-            for (int k = 0; k < D; ++k) col[k] = cw[k];
+            for (int x = 0; x < R; ++x) { const double2 v = zr[x]; z[2 * x] = v.x; z[2 * x + 1] = v.y; }
+            double f0, f1;
+            tame_rank2_F<R>(cw, z, f0, f1);
+            sm.Fs[0][lane] = make_double2(f0, f1);
+            __syncwarp();
+            tame_rank2_apply<R>(cw, z, f0, f1, sm.Fs[0], 1.0, R00, R01, R11);
         }
-        t_gj += clock64() - cg0;
-
-        // ---- factorisation rule -> row c of the new covariance in crow[]
-        double crow[D];
-        if (P.mode == 2 /*BAD*/) {
-#pragma unroll
-            for (int k = 0; k < D; ++k)
-                if ((k < 2) != (c < 2)) col[k] = 0.0;
-        }
-        if (c < D) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) sm.Cm[k * DP + c] = col[k];
-        }
-        __syncwarp();
-        if (c < D) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                double rv = sm.Cm[c * DP + k];
-                crow[k] = (P.mode == 0) ? rv : (0.5 * (rv + col[k]) + ((k == c) ? 1e-6 : 0.0));
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) crow[k] = 0.0;
-        }
-
-        // ---- (i, t-1): check the early look, spin only if the predecessor is not ahead
-        if (has_prev) {
-            int spins = 0;
-            const long long c0 = clock64();
-            for (;;) {
-                const bool ok = (c >= D) ||
-                    (((unsigned long long)__double_as_longlong(hv.x) ^ (unsigned long long)__double_as_longlong(hv.y)) == magic);
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (++spins > TAME_SPIN_LIMIT) { if (lane == 0) atomicExch(P.abort_flag, 1); break; }
-                if ((spins & 1023) == 0 && *((volatile int*)P.abort_flag)) break;
-                if (c < D) hv = tame_ld_volatile2(hand_prev + (size_t)i * T * D);
-            }
-            if (c < D) sm.mprev[c] = hv.x;
-            wait_hand += clock64() - c0;
-        }
-        __syncwarp();
-
-        // ---- natural parameter
-        double hval = 0.0;
+        // ---- cw = raw C_i.  Mean (factorisation rule applied to the row), damped write, hand-over
         {
-            // all lanes run the two AR mat-vecs (lanes >= D on row D-1, result discarded): no divergent region, and
-            // three partial sums each so the dependent FMA chains are D/3 long
-            const int cc = min(c, D - 1);
-            double p0 = 0.0, p1 = 0.0, p2 = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0;
-            if (has_prev) {
+            double h[D];
+            const double2* hv2 = reinterpret_cast<const double2*>(sm.hvec);
 #pragma unroll
-                for (int k = 0; k + 2 < D; k += 3) {
-                    p0 = fma(cstQP[k * D + cc], sm.mprev[k], p0);
-                    p1 = fma(cstQP[(k + 1) * D + cc], sm.mprev[k + 1], p1);
-                    p2 = fma(cstQP[(k + 2) * D + cc], sm.mprev[k + 2], p2);
-                }
-#pragma unroll
-                for (int k = (D / 3) * 3; k < D; ++k) p0 = fma(cstQP[k * D + cc], sm.mprev[k], p0);
-            }
-            if (has_next) {
-#pragma unroll
-                for (int k = 0; k + 2 < D; k += 3) {
-                    n0 = fma(cstPQ[k * D + cc], sm.mnext[k], n0);
-                    n1 = fma(cstPQ[(k + 1) * D + cc], sm.mnext[k + 1], n1);
-                    n2 = fma(cstPQ[(k + 2) * D + cc], sm.mnext[k + 2], n2);
-                }
-#pragma unroll
-                for (int k = (D / 3) * 3; k < D; ++k) n0 = fma(cstPQ[k * D + cc], sm.mnext[k], n0);
-            }
-            hval = hb + ((c >= 2 && c < D) ? sm.hin[c - 2] : 0.0);
-            hval += (p0 + p1) + p2;          // Qinv Phi mu_{t-1}      (structured_mf.py:258)
-            hval += (n0 + n1) + n2;          // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
-            if (c < D) sm.hvec[c] = hval;
-        }
-        __syncwarp();
-
-        // ---- mean, damped write, hand-over
-        if (c < D) {
+            for (int k = 0; k < D / 2; ++k) { const double2 v = hv2[k]; h[2 * k] = v.x; h[2 * k + 1] = v.y; }
             double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+            if (mode == 2) {                                                         // structured_mf.py:270-273
+                if (lo) { m0 = cw[0] * h[0]; m1 = cw[1] * h[1]; }
+                else {
 #pragma unroll
-            for (int k = 0; k + 2 < D; k += 3) {
-                m0 = fma(crow[k], sm.hvec[k], m0);
-                m1 = fma(crow[k + 1], sm.hvec[k + 1], m1);
-                m2 = fma(crow[k + 2], sm.hvec[k + 2], m2);
-            }
+                    for (int k = 2; k < D; ++k) {
+                        if (k % 3 == 0) m0 = fma(cw[k], h[k], m0); else if (k % 3 == 1) m1 = fma(cw[k], h[k], m1); else m2 = fma(cw[k], h[k], m2);
+                    }
+                }
+            } else {
 #pragma unroll
-            for (int k = (D / 3) * 3; k < D; ++k) m0 = fma(crow[k], sm.hvec[k], m0);
-            const double mu = (m0 + m1) + m2;
-            const double mnew = lr * mu + om * mo;
-            tame_st_cg(P.Xm + ((size_t)i * T + t) * D + c, mnew);
-            if (has_next || (FUSED && P.npeers > 0)) {
-                const unsigned long long tag = (unsigned long long)__double_as_longlong(mnew) ^ magic;
-                const double2 slotv = make_double2(mnew, __longlong_as_double((long long)tag));
-                const size_t off = (size_t)i * T * D + (size_t)t * D + c;
-                __stcg(P.hand + off, slotv);
-                if (FUSED) {
-                    for (int pr = 0; pr < P.npeers; ++pr) __stcg(P.hand_peer[pr] + off, slotv);     // NVLink peer stores
+                for (int k = 0; k < D; ++k) {
+                    if (k % 3 == 0) m0 = fma(cw[k], h[k], m0); else if (k % 3 == 1) m1 = fma(cw[k], h[k], m1); else m2 = fma(cw[k], h[k], m2);
                 }
             }
-            sm.mnew[c] = mnew;
+            double mu = (m0 + m1) + m2;
+            if (mode != 0) mu = fma(1e-6, hval, mu);                                 // (C + 1e-6 I) h   :277-279
+            const double mnew = lr * mu + om * mo;                                   // :282-284
+            if (act) {
+                tame_st_cg(P.Xm + xoff, mnew);
+                if (has_next || multi) {
+                    const unsigned long long tag = (unsigned long long)__double_as_longlong(mnew) ^ magic;
+                    const double2 slotv = make_double2(mnew, __longlong_as_double((long long)tag));
+                    __stcg(P.hand + xoff, slotv);
+                    if (FUSED) {
+                        for (int pr = 0; pr < P.npeers; ++pr) __stcg(P.hand_peer[pr] + xoff, slotv);     // NVLink peer stores
+                    }
+                }
+                if (c >= 2) sm.ring[i & RMASK][zpos] = mnew;
+                // raw covariance column -> global scratch; k_covblend applies mask / symmetrisation / jitter / damping
+                // (naive: only the diagonal 1 / (diag(P) + 1e-8) is kept, naive_mf.py:271-274)
+                const int l = (P.world == 1) ? i : tame_lrow(i, P.panel, P.world);
+                double* cr = P.Craw + ((size_t)l * T + t) * (D * D) + c;
+                if (mode != 0) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) __stcs(cr + k * D, cw[k]);
+                } else {
+                    __stcs(cr + c * D, 1.0 / (pdiag + 1e-8));
+                }
+            }
         }
+        // ---- down-date: node i+1 leaves with its old mean (independent of this node's mean: same instruction stream)
+        double zo[NV], g0 = 0.0, g1 = 0.0;
+        if (do_down) {
+            const double* mn = sm.inp[(i + 1) & IMASK].mold;
+            if (R % 2 == 0) {
+                const double2* mu2 = reinterpret_cast<const double2*>(mn + 2);          // U block
+                const double2* mv2 = reinterpret_cast<const double2*>(mn + 2 + R);      // V block
+#pragma unroll
+                for (int x = 0; x < R / 2; ++x) {
+                    const double2 v = mv2[x], u = mu2[x];
+                    zo[2 * x] = v.x; zo[2 * x + 1] = v.y; zo[R + 2 * x] = u.x; zo[R + 2 * x + 1] = u.y;
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < NV; ++x) zo[x] = mn[tame_zidx<R>(x)];
+            }
+            tame_rank2_F<R>(cw, zo, g0, g1);
+            sm.Fs[1][lane] = make_double2(g0, g1);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *((volatile int*)&sm.c_done) = i;
+        if (do_down) tame_rank2_apply<R>(cw, zo, g0, g1, sm.Fs[1], -1.0, R00, R01, R11);
+        ++ncell;
         // progress is only consumed by the streaming CTAs, at sub-block granularity: one fence per 32 nodes
         if (((i + 1) % TAME_SB) == 0 || i + 1 == i1) {
             __threadfence();
             __syncwarp();
             if (lane == 0) tame_st_release(P.progress + t, i + 1);
         }
-
-        // ---- covariance, damped write (coalesced through shared memory)
-        if (next_mine) tame_cp_async_wait<1>(); else tame_cp_async_wait<0>();   // node i's old covariance has landed
-        if (c < D) {
-            if (P.mode == 0) {
-                const double dinv = 1.0 / (pdiag + 1e-8);
-#pragma unroll
-                for (int k = 0; k < D; ++k) sm.Cf[k * D + c] = (k == c) ? dinv : 0.0;
-            } else {
-#pragma unroll
-                for (int k = 0; k < D; ++k) sm.Cf[k * D + c] = crow[k];     // exactly symmetric: [k][c] is conflict-free
-            }
-        }
-        __syncwarp();
-        {
-            double* cp = P.Xc + ((size_t)i * T + t) * D * D;
-#pragma unroll
-            for (int m = 0; m < NE; ++m) {
-                int e = lane + 32 * m;
-                if (e < D * D) __stcs(cp + e, lr * sm.Cf[e] + om * sm.cold[i & 1][e]);
-            }
-        }
-        // ---- totals with the new mean, window ring
-        tot_update(sm.mnew, 1.0);
-        if (lane < NV) sm.ring[i & (TAME_RING - 1)][lane] = tame_zof<R>(sm.mnew, lane);
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) *((volatile int*)&sm.c_done) = i;
     }
     if (probe) {
         dbg[2] = tame_globaltimer();
-        dbg[3] = (unsigned long long)wait_unit;
-        dbg[4] = (unsigned long long)wait_hand;
-        dbg[5] = (unsigned long long)t_gj;
-        dbg[6] = (unsigned long long)(i1 - i0);
-    }
-    if (c >= 2 && c < D) {
-        P.tot[(size_t)t * TOT + (c - 2)] = gy;
-#pragma unroll
-        for (int x = 0; x < NV; ++x) P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)] = Gc[x];
+        dbg[6] = (unsigned long long)ncell;
+        dbg[7] = (unsigned long long)wait_in;
     }
 }
 
+// One chain CTA: warps 0..WPC-1 are the chain warps of WPC consecutive time steps (one per SM sub-partition), warps
+// WPC..2*WPC-1 their helpers.
+template <int R, bool FUSED>
+__device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned char* smem_raw, int cta, int i0, int i1) {
+    using S = TameChainSmem<R>;
+    S* warps = reinterpret_cast<S*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < TAME_CHAIN_WPC) { warps[threadIdx.x].h_ready = i0 - 1; warps[threadIdx.x].c_done = i0 - 1; }
+    __syncthreads();
+    const bool is_helper = warp >= TAME_CHAIN_WPC;
+    const int wpair = warp - (is_helper ? TAME_CHAIN_WPC : 0);
+    if (wpair >= TAME_CHAIN_WPC) return;
+    const int t = cta * TAME_CHAIN_WPC + wpair;
+    if (t >= P.T) return;
+    if (is_helper) tame_chain_helper<R, FUSED>(P, warps[wpair], lane, t, i0, i1);
+    else tame_chain_warp<R, FUSED>(P, warps[wpair], lane, t, i0, i1);
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// k_covblend: X_cov[i,t] = lr * rule(C_raw) + (1 - lr) * X_cov[i,t] for the rank's own nodes, one thread per element.
+//   good : rule(C) = (C + C')/2 + 1e-6 I                        structured_mf.py:276-277, damping :285-287
+//   bad  : the 2 x 2r cross blocks are zeroed first             :270-273
+//   naive: rule = diag(1 / (diag(P) + 1e-8)), kept on the diagonal of the scratch     naive_mf.py:271-274, 280-282
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) k_covblend(TameParams P) {
+    constexpr int D = 2 + 2 * R, DD = D * D;
+    const size_t total = (size_t)P.nloc * P.T * DD;
+    const double lr = P.lr, om = 1.0 - P.lr;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t cell = idx / DD;
+        const int e = (int)(idx - cell * DD), row = e / D, col = e - row * D;
+        const int l = (int)(cell / P.T), t = (int)(cell - (size_t)l * P.T);
+        const int i = tame_grow(l, P.panel, P.world, P.rank);
+        const double* cr = P.Craw + cell * DD;
+        double cf;
+        if (P.mode == 0) cf = (row == col) ? __ldcs(cr + e) : 0.0;
+        else {
+            const bool masked = (P.mode == 2) && ((row < 2) != (col < 2));
+            cf = masked ? 0.0 : 0.5 * (__ldcs(cr + e) + __ldcs(cr + col * D + row));
+            if (row == col) cf += 1e-6;
+        }
+        double* xc = P.Xc + ((size_t)i * P.T + t) * DD + e;
+        *xc = lr * cf + om * *xc;
+    }
+}
 
 // stand-alone chain launch over one 64-node block (multi-GPU path); cooperative, grid = ceil(T/8)
 template <int R>
@@ -966,7 +1109,6 @@ template <int R, int RW>
 __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(8 * RW == TAME_SB, "a streaming unit is one sub-block of rows");
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.dbg[7] = tame_globaltimer();
     if ((int)blockIdx.x < P.n_chain_ctas) {
         tame_chain_body<R, true>(P, smem_raw, blockIdx.x, 0, P.n);
         return;
@@ -1530,6 +1672,7 @@ struct TameOps {
     void (*totals)(const TameParams&, double* partial, int NS, cudaStream_t);
     void (*contract)(const TameParams&, int k0, int k1, int j0, int j1, int tri, int accumulate, cudaStream_t);
     cudaError_t (*chain)(const TameParams&, int i0, int i1, cudaStream_t);
+    void (*covblend)(const TameParams&, cudaStream_t);
     cudaError_t (*sweep_fused)(const TameParams&, cudaStream_t);
     int (*sweep_capacity)();
     int (*chain_max_T)();

@@ -1,6 +1,7 @@
 // tame_ops.cu -- instantiates the kernels of tame_kernels.cuh for one latent dimension (-DTAME_R=r) and
 // exports their launchers through a function table; tame_api.cu picks the table by cfg.r.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -14,6 +15,37 @@ namespace {
 constexpr int R = TAME_R;
 constexpr int RW = 4;
 
+// Kernel attributes (opt-in shared memory) and occupancy figures are per DEVICE: one flag / value per ordinal, so that a
+// process driving several GPUs (drop-in `devices=`, tame_fit_batch over devices) configures each of them.
+constexpr int MAX_DEV = 64;
+struct PerDevice {
+    std::atomic<int> v[MAX_DEV];
+    PerDevice() { for (auto& x : v) x.store(-1); }
+};
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < MAX_DEV) ? dev : 0;
+}
+int device_sms(int dev) {
+    static PerDevice sms;
+    int s = sms.v[dev].load();
+    if (s < 0) {
+        cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev);
+        sms.v[dev].store(s);
+    }
+    return s;
+}
+// runs `cfg` once per device (idempotent, so a race between two threads only repeats it)
+template <class F>
+void once_per_device(PerDevice& flag, F cfg) {
+    const int dev = current_device();
+    if (flag.v[dev].load() < 0) {
+        cfg();
+        flag.v[dev].store(1);
+    }
+}
+
 void launch_totals(const TameParams& P, double* partial, int NS, cudaStream_t st) {
     k_totals_partial<R><<<dim3(P.T, NS), 320, 0, st>>>(P, partial, NS);
     k_totals_final<R><<<P.T, 128, 0, st>>>(P, partial, NS);
@@ -24,25 +56,20 @@ void launch_contract(const TameParams& P, int k0, int k1, int j0, int j1, int tr
     if (k1 <= k0 || j1 <= j0) return;
     dim3 grid((P.T + 31) / 32, (k1 - k0 + 8 * RW - 1) / (8 * RW));
     constexpr size_t smem = TameStream<R, RW>::SMEM;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_contract<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static PerDevice configured;
+    once_per_device(configured, [] { cudaFuncSetAttribute(k_contract<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     k_contract<R, RW><<<grid, 256, smem, st>>>(P, k0, k1, j0, j1, tri, accumulate);
     tame_count_launch(1);
 }
 
-size_t chain_smem_bytes() { return 2 * (2 + 2 * R) * (2 + 2 * R) * sizeof(double) + TAME_CHAIN_WPC * sizeof(TameChainSmem<R>); }
+size_t chain_smem_bytes() { return TAME_CHAIN_WPC * sizeof(TameChainSmem<R>); }
 
 cudaError_t launch_chain(const TameParams& P, int i0, int i1, cudaStream_t st) {
-    static bool configured = false;
+    static PerDevice configured;
     const size_t smem = chain_smem_bytes();
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    cudaError_t ce = cudaSuccess;
+    once_per_device(configured, [&] { ce = cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    if (ce != cudaSuccess) return ce;
     TameParams p = P;
     void* args[] = {(void*)&p, (void*)&i0, (void*)&i1};
     dim3 grid((P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC);
@@ -50,30 +77,42 @@ cudaError_t launch_chain(const TameParams& P, int i0, int i1, cudaStream_t st) {
     return cudaLaunchCooperativeKernel((void*)k_chain<R>, grid, dim3(2 * TAME_CHAIN_WPC * 32), args, smem, st);
 }
 
+void launch_covblend(const TameParams& P, cudaStream_t st) {
+    const size_t total = (size_t)P.nloc * P.T * (2 + 2 * R) * (2 + 2 * R);
+    if (total == 0) return;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)device_sms(current_device()) * 16);
+    k_covblend<R><<<blocks, 256, 0, st>>>(P);
+    tame_count_launch(1);
+}
+
 size_t sweep_smem_bytes() { return chain_smem_bytes() > TameStream<R, RW>::SMEM ? chain_smem_bytes() : TameStream<R, RW>::SMEM; }
 
 // co-resident CTAs of k_sweep on the current device
 int sweep_capacity() {
-    int dev = 0, sms = 0, per = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_sweep<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep<R, RW>, 256, sweep_smem_bytes());
-    return sms * per;
+    static PerDevice cap;
+    const int dev = current_device();
+    int c = cap.v[dev].load();
+    if (c < 0) {
+        int per = 0;
+        cudaFuncSetAttribute(k_sweep<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep<R, RW>, 256, sweep_smem_bytes());
+        c = device_sms(dev) * per;
+        cap.v[dev].store(c);
+    }
+    return c;
 }
 
 cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
-    static int capacity = -1;
-    if (capacity < 0) capacity = sweep_capacity();
+    const int capacity = sweep_capacity();
     TameParams p = P;
     p.n_chain_ctas = (P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC;
     const int nunits = ((P.n + TAME_SB - 1) / TAME_SB) * ((P.T + 31) / 32) * P.nparts;
     int workers = capacity - p.n_chain_ctas < nunits ? capacity - p.n_chain_ctas : nunits;
     if (workers < 1) return cudaErrorLaunchOutOfResources;
-    // small problems: the chain (n nodes x ~4 us) outlasts the streaming (16 n^2 T bytes at ~30 GB/s per CTA) unless there are
-    // fewer than ~n T / 7500 streaming CTAs; do not occupy more SMs than that, so that independent fits (tame_fit_batch) run
-    // side by side.  Any count >= 1 is correct: units are claimed dynamically and in order.
-    const long want = ((long)P.n * P.T + 4999) / 5000 + 1;
+    // small problems: the chain (n nodes x ~1.5 us) outlasts the streaming (16 n^2 T bytes at ~30 GB/s per CTA) unless there
+    // are fewer than ~n T / 2500 streaming CTAs; do not occupy many more SMs than that, so that independent fits
+    // (tame_fit_batch) run side by side.  Any count >= 1 is correct: units are claimed dynamically and in order.
+    const long want = ((long)P.n * P.T + 1499) / 1500 + 2;
     if ((long)workers > want) workers = (int)want;
     void* args[] = {(void*)&p};
     tame_count_launch(1);
@@ -81,12 +120,17 @@ cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
 }
 
 int chain_max_T() {
-    int dev = 0, sms = 0, per = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<R>, 2 * TAME_CHAIN_WPC * 32, chain_smem_bytes());
-    return sms * per * TAME_CHAIN_WPC;
+    static PerDevice cap;
+    const int dev = current_device();
+    int c = cap.v[dev].load();
+    if (c < 0) {
+        int per = 0;
+        cudaFuncSetAttribute(k_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<R>, 2 * TAME_CHAIN_WPC * 32, chain_smem_bytes());
+        c = device_sms(dev) * per * TAME_CHAIN_WPC;
+        cap.v[dev].store(c);
+    }
+    return c;
 }
 
 constexpr int LL_RW = 2, LL_NW = 16;      // k_llmse tile: 16 warps x 2 rows
@@ -103,12 +147,11 @@ struct LlmseMma<RR, true> {
     static bool launch(const TameParams& P, double* partial, int* nblocks, int symmetric, cudaStream_t st) {
         dim3 grid((P.T + 31) / 32, (P.nloc + 15) / 16);
         constexpr size_t smem = TameMma<RR>::SMEM;
-        static bool configured = false;
-        if (!configured) {
+        static PerDevice configured;
+        once_per_device(configured, [] {
             cudaFuncSetAttribute(k_llmse_mma<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(k_llmse_mma<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = true;
-        }
+        });
         if (symmetric) k_llmse_mma<RR, true><<<grid, 256, smem, st>>>(P, partial);
         else k_llmse_mma<RR, false><<<grid, 256, smem, st>>>(P, partial);
         *nblocks = grid.x * grid.y;
@@ -132,15 +175,13 @@ void launch_llmse(const TameParams& P, double* partial, int* nblocks, int symmet
     dim3 grid((P.T + 31) / 32, (P.nloc + 31) / 32);
     constexpr size_t smem = TameStream<R, RW>::SMEM;      // ring PD x LL_RW x 512 x 16 B == PD x RW x 256 x 16 B
     static_assert(LL_RW * LL_NW == RW * 8, "same ring footprint");
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    once_per_device(configured, [] {
         cudaFuncSetAttribute(k_llmse<R, LL_RW, LL_NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_llmse<R, LL_RW, LL_NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    });
     // split the partner range over grid.z when the (row tile x time slice) grid alone would leave SMs idle
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = device_sms(current_device());
     const int base = grid.x * grid.y;
     grid.z = (base >= 3 * sms) ? 1 : std::min(4, (3 * sms + base - 1) / base);
     if (symmetric) k_llmse<R, LL_RW, LL_NW, true><<<grid, LL_NW * 32, smem, st>>>(P, partial);
@@ -158,5 +199,5 @@ void launch_cellterms(const TameParams& P, double logdetS0, double logdetQ, doub
 #define TAME_CAT2(a, b) a##b
 #define TAME_CAT(a, b) TAME_CAT2(a, b)
 extern const TameOps TAME_CAT(tame_ops_r, TAME_R) = {
-    R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, launch_sweep_fused, sweep_capacity, chain_max_T,
+    R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, launch_covblend, launch_sweep_fused, sweep_capacity, chain_max_T,
     launch_llmse, launch_cellterms, llmse_blocks};
