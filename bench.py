@@ -367,6 +367,15 @@ def run_ours(args, shape):
     probes = (C.c_uint64 * 16)()
     lib.tame_debug_probes(h, probes)
     probes = list(probes)
+    if os.environ.get("TAME_TRACE") and rank == 0:
+        nsb = (n + 31) // 32
+        tr = (C.c_uint64 * (22 * nsb))()
+        if lib.tame_debug_trace(h, tr, 22 * nsb) == 0:
+            tr = np.array(list(tr), dtype=np.float64)
+            t0_ = float(probes[0])
+            hw, ut, rl = tr[:2 * nsb].reshape(nsb, 2), tr[2 * nsb:6 * nsb].reshape(nsb, 4), tr[6 * nsb:].reshape(nsb, 16)
+            # columns (us since the chain's start): helper starts waiting, helper released | unit claimed, upper done, group-0 urgent, group-0 stamped
+            np.save(os.environ.get("TAME_TRACE_OUT", "gpurun_out/trace.npy"), np.concatenate([(hw - t0_) / 1e3, (ut - t0_) / 1e3, (rl - t0_) / 1e3], 1))
     ms = e0.elapsed_time(e1)
     launches = lib.tame_launch_count() - launches0
     if world > 1:

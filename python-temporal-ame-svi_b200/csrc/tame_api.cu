@@ -122,6 +122,7 @@ struct tame_handle {
     void* peer_base[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // IPC mappings of the peers' hand buffers
     int npeers = 0;
     unsigned long long* dbg = nullptr;
+    unsigned long long* trace = nullptr;
     int NS = 1, nb_ll = 0, nb_cell = 0;
     double* out6_pinned = nullptr;
     int* abort_pinned = nullptr;
@@ -412,8 +413,13 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     const size_t nunits = (size_t)((n + TAME_SB - 1) / TAME_SB) * ((T + 31) / 32);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_counter, sizeof(int));
     if (e == cudaSuccess) e = dalloc((void**)&h->dbg, sizeof(unsigned long long) * 16);
+    if (getenv("TAME_TRACE")) {
+        const size_t nb = sizeof(unsigned long long) * 22 * ((n + TAME_SB - 1) / TAME_SB);
+        if (e == cudaSuccess) e = dalloc((void**)&h->trace, nb);
+        if (e == cudaSuccess) e = cudaMemset(h->trace, 0, nb);
+    }
     if (e == cudaSuccess) e = dalloc((void**)&h->hand, sizeof(double2) * (size_t)n * T * d);
-    if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits * h->nparts);
+    if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits * h->nparts * TAME_NG);
     if (e == cudaSuccess) e = dalloc((void**)&h->red6, sizeof(double) * 6);
     if (e == cudaSuccess) e = dalloc((void**)&h->out6, sizeof(double) * 6);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out6_pinned, sizeof(double) * 6);
@@ -426,7 +432,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     CK(cudaMemset(h->cursor, 0, sizeof(int) * TAME_MAX_PARTS));
     CK(cudaMemset(h->dbg, 0, sizeof(unsigned long long) * 16));
     CK(cudaMemset(h->hand, 0, sizeof(double2) * (size_t)n * T * d));
-    CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits * h->nparts));
+    CK(cudaMemset(h->unit_done, 0, sizeof(int) * nunits * h->nparts * TAME_NG));
     {
         const char* v = getenv("TAME_SWEEP");   // "panel" forces the stream-ordered per-panel path (debug / comparison)
         h->fused = (world == 1) && !(v && strcmp(v, "panel") == 0);
@@ -439,7 +445,9 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.lr = cfg->lr;
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.Craw = h->Craw; P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
-    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.nparts = h->nparts; P.cursor = h->cursor; P.npeers = 0;
+    P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.trace = h->trace; P.nparts = h->nparts; P.cursor = h->cursor; P.npeers = 0;
+    P.probe_t = T - 1;
+    if (const char* v = getenv("TAME_PROBE_T")) P.probe_t = std::max(0, std::min(T - 1, atoi(v)));
     for (int k = 0; k < 7; ++k) P.hand_peer[k] = nullptr;
     CK(cudaDeviceSynchronize());      // the zeroed hand-over slots must be in place before any peer can write into them
 
@@ -459,7 +467,7 @@ int tame_destroy(tame_handle* h) {
     for (int k = 0; k < h->npeers; ++k) if (h->peer_base[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
     for (void* p : {(void*)h->Craw, (void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
-                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->sym_flag, (void*)h->cursor})
+                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->trace, (void*)h->sym_flag, (void*)h->cursor})
         if (p) cudaFree(p);
     if (h->out6_pinned) cudaFreeHost(h->out6_pinned);
     if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
@@ -824,6 +832,16 @@ int tame_debug_probes(tame_handle* h, uint64_t* out16_host) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out16_host, h->dbg, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
+    return TAME_OK;
+}
+
+int tame_debug_trace(tame_handle* h, uint64_t* out_host, int32_t n_entries) {
+    if (!h || !out_host) return fail(TAME_EINVAL, "null argument");
+    if (!h->trace) return fail(TAME_ESTATE, "tracing is off (set TAME_TRACE=1 before tame_create)");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const int have = 22 * ((h->P.n + TAME_SB - 1) / TAME_SB);
+    CK(cudaMemcpy(out_host, h->trace, sizeof(unsigned long long) * std::min(have, (int)n_entries), cudaMemcpyDeviceToHost));
     return TAME_OK;
 }
 

@@ -31,6 +31,7 @@
 #define TAME_SPIN_LIMIT (1 << 24)   // streaming workers' poll bound (the chain's waits are time-bounded, TAME_WATCHDOG_NS)
 #define TAME_SB 32           // sub-block of the fused sweep: rows per streaming unit, push granularity
 #define TAME_MAX_PARTS 4     // column parts per streaming unit (k_sweep): 1..TAME_MAX_PARTS
+#define TAME_NG 4            // a streaming unit's 32 time steps are released / stamped as TAME_NG groups of 8
 #define TAME_REFRESH 64      // the chain re-inverts the precision from scratch every TAME_REFRESH nodes (rank-2 updates between)
 
 struct TameParams {
@@ -47,6 +48,7 @@ struct TameParams {
     int* progress;            // (T) nodes finished in this sweep by the warp of time t
     int* abort_flag;
     // fused sweep (k_sweep): work distribution between the chain CTAs and the streaming CTAs
+    unsigned long long* trace; // (2 * sub-blocks) optional: when the helper of t=0 started / stopped waiting for each sub-block's unit
     unsigned long long* dbg;  // 16 timing slots (ns / cycles) written by the first and last time-step warps
     double2* hand;            // (n,T,D) hand-over slots {new mean, tag}: the flag travels with the data
     double2* hand_peer[7];    // the other ranks' `hand` buffers (CUDA IPC peer pointers over NVLink); npeers entries
@@ -57,6 +59,7 @@ struct TameParams {
     int* cursor;              // (TAME_MAX_PARTS) column position last published by a streaming CTA of each column part
     int nparts;               // column parts per streaming unit (H holds nparts slabs of nloc*T*2R partial sums)
     int n_chain_ctas;
+    int probe_t;              // time step of the second probe slot (dbg[8..15]); default T-1
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -195,7 +198,8 @@ struct TameStream {
 template <int R, int RW>
 __device__ __forceinline__ void tame_stream_cols(const TameParams& P, unsigned char* smem_raw, const double* const (&yrow)[RW],
                                                  const bool (&rv)[RW], int kw, int t0, int jb, int je, bool tri,
-                                                 double (&accA)[RW][R], double (&accB)[RW][R], int* cursor = nullptr) {
+                                                 double (&accA)[RW][R], double (&accB)[RW][R], int* cursor = nullptr,
+                                                 bool lane_on = true) {
     using TS = TameStream<R, RW>;
     constexpr int D = TS::D, JC = TS::JC, PD = TS::PD, RS = TS::RS;
     static_assert(JC == PD, "ring slot == position in chunk");
@@ -210,7 +214,7 @@ __device__ __forceinline__ void tame_stream_cols(const TameParams& P, unsigned c
 #pragma unroll
         for (int rr = 0; rr < RW; ++rr) {
             const int k = kw + rr;
-            const bool ok = rv[rr] && (j < je) && (tri ? (j > k) : (j != k));
+            const bool ok = lane_on && rv[rr] && (j < je) && (tri ? (j > k) : (j != k));
             tame_cp_async16(&Yr[slot][rr][tid], yrow[rr] + (size_t)min(j, P.n - 1) * jstride, ok);
         }
     };
@@ -444,6 +448,7 @@ __device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rowb
 #define TAME_LA 4            // look-ahead of the helper's global loads, in nodes
 #define TAME_NSLOT 8         // depth of the staging ring (power of two, >= TAME_LA + 2)
 #define TAME_NINP 4          // depth of the helper -> chain mailbox (power of two, >= TAME_NL + 2)
+#define TAME_MR 16           // depth of the intra-CTA hand-over ring (self-validating slots; the global slot is the fallback)
 #define TAME_WMAX 96         // widest inline window (partners)
 #define TAME_WATCHDOG_NS 4000000000ull
 
@@ -471,6 +476,7 @@ struct __align__(16) TameChainSmem {
     double2 Fs[2][32];                              // F = M J' of the up-date / down-date, one row per lane
     double rowb[TAME_GJ_ROWB(D)];
     double hvec[D], mprev[D], hin[NV];
+    double2 mring[TAME_MR][D];                      // chain -> helper of the next time step in the same CTA: {new mean, tag}
     int h_ready;                                    // last node whose inputs the helper has published
     int c_done;                                     // last node the chain warp has finished
     int pad_[2];
@@ -478,6 +484,20 @@ struct __align__(16) TameChainSmem {
 static_assert(sizeof(TameChainSmem<1>) % 16 == 0 && sizeof(TameChainSmem<2>) % 16 == 0 && sizeof(TameChainSmem<3>) % 16 == 0 &&
               sizeof(TameChainSmem<4>) % 16 == 0 && sizeof(TameChainSmem<8>) % 16 == 0, "per-warp chain block must stay 16-byte aligned");
 static_assert(TAME_LA + 2 <= TAME_NSLOT && TAME_NL + 2 <= TAME_NINP, "mailbox depth");
+
+// panel-cyclic ownership of consecutive nodes without integer divisions: rem = k % panel, pw = (k / panel) % world,
+// lb = (k / panel) / world; owned = (pw == rank), local row = lb * panel + rem
+struct TameOwn {
+    int rem, pw, lb;
+    __device__ __forceinline__ void init(int k, int panel, int world) {
+        const int b = k / panel;
+        rem = k - b * panel; pw = b % world; lb = b / world;
+    }
+    __device__ __forceinline__ void next(int panel, int world) {
+        if (++rem == panel) { rem = 0; if (++pw == world) { pw = 0; ++lb; } }
+    }
+    __device__ __forceinline__ int lrow(int panel) const { return lb * panel + rem; }
+};
 
 // time-bounded spinning: every 1024 failed polls look at the abort flag and at the clock
 struct TameSpin {
@@ -550,7 +570,8 @@ __device__ __forceinline__ void tame_rank2_apply(double (&cw)[2 + 2 * R], const 
 // helper warp of time step t
 // ------------------------------------------------------------------------------------------------------
 template <int R, bool FUSED>
-__device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChainSmem<R>& sm, int lane, int t, int i0, int i1) {
+__device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChainSmem<R>& sm, const TameChainSmem<R>* pv, int lane, int t,
+                                                  int i0, int i1) {
     using S = TameChainSmem<R>;
     constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP;
     constexpr int WSB = FUSED ? TAME_SB : TAME_WIN, WBACK = FUSED ? 2 : 0, NWS = FUSED ? 3 : 2;
@@ -564,12 +585,22 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
     const size_t slab = (size_t)P.nloc * T * NV;
     const double2* hand_prev = P.hand + (size_t)max(t - 1, 0) * D + cc;     // + i*T*D : slot of (i, t-1), component cc
     const double2* hand_mine = P.hand + (size_t)t * D + cc;
-    auto owned = [&](int k) { return !multi || tame_owned(k, P.panel, P.world, P.rank); };
-    auto lrow = [&](int k) { return (P.world == 1) ? k : tame_lrow(k, P.panel, P.world); };
     auto window_lo = [&](int k) { return max(i0, (k / WSB - WBACK) * WSB); };
     auto tag_ok = [&](const double2& v) {
         return ((unsigned long long)__double_as_longlong(v.x) ^ (unsigned long long)__double_as_longlong(v.y)) == magic;
     };
+    // (i, t-1) from a chain warp of the same CTA comes through its shared-memory ring (tag keyed by the node as well)
+    const bool use_ring = (pv != nullptr);
+    auto rtag_ok = [&](const double2& v, int k) {
+        return ((unsigned long long)__double_as_longlong(v.x) ^ (unsigned long long)__double_as_longlong(v.y)) ==
+               magic + (unsigned long long)(unsigned)k * 0x9E3779B97F4A7C15ull;
+    };
+    // ownership of the three node streams this warp walks: k (current), k-1-NL (folded into the totals), k+1+LA (staged)
+    TameOwn own_k, own_f, own_s;
+    own_k.init(i0, P.panel, P.world);
+    own_f.init(i0, P.panel, P.world);
+    own_s.init(i0, P.panel, P.world);
+    auto is_mine = [&](const TameOwn& o) { return !multi || o.pw == P.rank; };
 
     // rows cc of Qinv Phi and Phi' Qinv (AR(1) terms of h, structured_mf.py:258,264) and the constant part of diag(P)
     double qp[D], pq[D];
@@ -616,18 +647,18 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
 
     // stage ALL global inputs of node k (cp.async; the caller commits one group per loop iteration).  At the first node of a
     // sub-block the stamp of its streaming unit (static partner part H) is awaited first.
-    auto stage = [&](int k) {
+    auto stage = [&](int k, bool mine_s, int l) {
         typename S::Stage& s = sm.st[k & SMASK];
         const size_t cell = (size_t)k * T + t;
         const double* xm = P.Xm + cell * D;
         if (lane < D / 2) tame_cp_async16(&s.mold[2 * lane], xm + 2 * lane, true);
-        if (!owned(k)) {
+        if (!mine_s) {
             if (act) tame_cp_async16(&s.hand[c], hand_mine + (size_t)k * T * D, true);
             return;
         }
         if (has_prev && act) tame_cp_async16(&s.hand[c], hand_prev + (size_t)k * T * D, true);
         if (has_next && lane >= 16 && lane < 16 + D / 2) tame_cp_async16(&s.mnext[2 * (lane - 16)], xm + D + 2 * (lane - 16), true);
-        const int l = lrow(k), wlo = window_lo(k);
+        const int wlo = window_lo(k);
         const double* yb = P.Y + (((size_t)l * P.n + wlo) * T + t) * 2;
 #pragma unroll
         for (int u = 0; u < NWS; ++u) {
@@ -636,17 +667,19 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
         }
         if (FUSED && (k % TAME_SB) == 0) {
             const long long c0 = clock64();
+            if (P.trace != nullptr && t == 0 && lane == 0) P.trace[2 * (k / TAME_SB)] = tame_globaltimer();
             int ok = 1;
             if (lane == 0) {
-                const int* flag = P.unit_done + ((l / TAME_SB) * nslices + (t >> 5)) * P.nparts;
+                const int* flag = P.unit_done + (size_t)((l / TAME_SB) * nslices + (t >> 5)) * P.nparts * TAME_NG + ((t >> 3) & (TAME_NG - 1));
                 TameSpin sp;
                 for (int part = 0; part < P.nparts && ok; ++part)
-                    while (tame_ld_acquire(flag + part) != P.epoch)
+                    while (tame_ld_acquire(flag + part * TAME_NG) != P.epoch)
                         if (sp.expired(P.abort_flag)) { ok = 0; break; }
             }
             ok = __shfl_sync(0xffffffffu, ok, 0);
             __syncwarp();
             wait_unit += clock64() - c0;
+            if (P.trace != nullptr && t == 0 && lane == 0) P.trace[2 * (k / TAME_SB) + 1] = tame_globaltimer();
             if (!ok) { alive = false; return; }
         }
         const size_t lcell = (size_t)l * T + t;
@@ -658,11 +691,12 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
     };
 
     for (int u = 0; u <= LA; ++u) {
-        if (alive && i0 + u < i1) stage(i0 + u);
+        if (alive && i0 + u < i1) stage(i0 + u, is_mine(own_s), own_s.lrow(P.panel));
+        own_s.next(P.panel, P.world);
         tame_cp_async_commit();
     }
     for (int k = i0; k < i1 && alive; ++k) {
-        const bool mine = owned(k);
+        const bool mine = is_mine(own_k);
         tame_cp_async_wait<LA>();
         __syncwarp();
         const typename S::Stage& s = sm.st[k & SMASK];
@@ -670,12 +704,13 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
         // ---- totals: node k-1-NL enters with its new mean (its z is in the ring), node k leaves with its old mean
         const int jf = k - 1 - NL;
         if (jf >= i0) {
-            if (owned(jf)) {
+            if (is_mine(own_f)) {
                 const long long c0 = clock64();
                 if (!tame_wait_smem(&sm.c_done, jf, lane, P.abort_flag)) { alive = false; break; }
                 wait_chain += clock64() - c0;
             }
             tot_update(sm.ring[jf & RMASK], FalseT{}, 1.0);
+            own_f.next(P.panel, P.world);
         }
         tot_update(s.mold, TrueT{}, -1.0);
 
@@ -730,11 +765,27 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
                 for (int q = (D / 3) * 3; q < D; ++q) n0 = fma(pq[q], s.mnext[q], n0);
                 hval += (n0 + n1) + n2;                                  // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
             }
-            // ---- (k, t-1): the staged look at its hand-over slot; poll only if the predecessor is not that far ahead
+            // ---- (k, t-1), cheapest source first: the ring of the neighbouring chain warp (same CTA) if it is already
+            // there; the staged look at the global hand-over slot (valid when the predecessor is TAME_LA+ nodes ahead, which
+            // also covers a ring slot that has been overwritten since); wait for the ring; poll the global slot
             if (has_prev) {
-                double2 hv = s.hand[cc];
-                if (!__all_sync(0xffffffffu, !act || tag_ok(hv))) {
-                    const long long c0 = clock64();
+                double2 hv = make_double2(0.0, 0.0);
+                bool got = false;
+                const long long c0 = clock64();
+                if (use_ring && *((volatile const int*)&pv->c_done) >= k) {
+                    hv = pv->mring[k & (TAME_MR - 1)][cc];
+                    got = __all_sync(0xffffffffu, !act || rtag_ok(hv, k));
+                }
+                if (!got) {
+                    hv = s.hand[cc];
+                    got = __all_sync(0xffffffffu, !act || tag_ok(hv));
+                }
+                if (!got && use_ring) {
+                    if (!tame_wait_smem(&pv->c_done, k, lane, P.abort_flag)) { alive = false; break; }
+                    hv = pv->mring[k & (TAME_MR - 1)][cc];
+                    got = __all_sync(0xffffffffu, !act || rtag_ok(hv, k));
+                }
+                if (!got) {
                     TameSpin sp;
                     for (;;) {
                         if (act) hv = tame_ld_volatile2(hand_prev + (size_t)k * T * D);
@@ -743,14 +794,45 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
                         if (lane == 0) ex = sp.expired(P.abort_flag) ? 1 : 0;
                         if (__shfl_sync(0xffffffffu, ex, 0)) { alive = false; break; }
                     }
-                    wait_hand += clock64() - c0;
                     if (!alive) break;
                 }
+                wait_hand += clock64() - c0;
                 if (act) sm.mprev[c] = hv.x;
             }
             __syncwarp();        // wbuf, mprev
-            // ---- partial window sum over the ring: lane = (partner phase, component pair); NPP pairs x PH phases = 32 lanes
-            {
+            // ---- partial window sum over the ring
+            if (R % 4 == 0) {
+                // lane = (partner phase, component quad): NGR quads x PH phases = 32 lanes; a quad lies in one half of z
+                constexpr int NGR = (NV / 4 > 0) ? NV / 4 : 1, PH = 32 / NGR;
+                const int gq = lane % NGR, ph = lane / NGR, x0 = 4 * gq;
+                const double* wsel = reinterpret_cast<const double*>(sm.wbuf) + ((x0 < R) ? 0 : 1);
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+                int jj = ph;
+                for (; jj + PH < cnt; jj += 2 * PH) {
+                    const double wa = wsel[2 * jj], wb = wsel[2 * (jj + PH)];
+                    const double2* za = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                    const double2* zb = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj + PH) & RMASK][x0]);
+                    const double2 za0 = za[0], za1 = za[1], zb0 = zb[0], zb1 = zb[1];
+                    a0 = fma(wa, za0.x, a0); a1 = fma(wa, za0.y, a1); a2 = fma(wa, za1.x, a2); a3 = fma(wa, za1.y, a3);
+                    b0 = fma(wb, zb0.x, b0); b1 = fma(wb, zb0.y, b1); b2 = fma(wb, zb1.x, b2); b3 = fma(wb, zb1.y, b3);
+                }
+                if (jj < cnt) {
+                    const double wa = wsel[2 * jj];
+                    const double2* za = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                    const double2 za0 = za[0], za1 = za[1];
+                    a0 = fma(wa, za0.x, a0); a1 = fma(wa, za0.y, a1); a2 = fma(wa, za1.x, a2); a3 = fma(wa, za1.y, a3);
+                }
+                a0 += b0; a1 += b1; a2 += b2; a3 += b3;
+#pragma unroll
+                for (int o = NGR; o < 32; o <<= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+                }
+                if (lane < NGR) { sm.hin[x0] = a0; sm.hin[x0 + 1] = a1; sm.hin[x0 + 2] = a2; sm.hin[x0 + 3] = a3; }
+            } else {
+                // lane = (partner phase, component pair); NPP pairs x PH phases = 32 lanes
                 constexpr int NPP = (R <= 1) ? 1 : (R <= 2) ? 2 : (R <= 4) ? 4 : 8, PH = 32 / NPP;
                 const int xp = min(lane % NPP, R - 1), ph = lane / NPP, x0 = 2 * xp;
                 const bool a0 = x0 < R, a1 = x0 + 1 < R;
@@ -828,15 +910,18 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
         }
         // ---- next inputs
         __syncwarp();
-        if (k + 1 + LA < i1) stage(k + 1 + LA);
+        if (k + 1 + LA < i1) stage(k + 1 + LA, is_mine(own_s), own_s.lrow(P.panel));
+        own_s.next(P.panel, P.world);
+        own_k.next(P.panel, P.world);
         tame_cp_async_commit();
     }
     // ---- drain: the last nodes' totals
     tame_cp_async_wait<0>();
     __syncwarp();
     for (int jf = max(i0, i1 - 1 - NL); jf < i1 && alive; ++jf) {
-        if (owned(jf) && !tame_wait_smem(&sm.c_done, jf, lane, P.abort_flag)) { alive = false; break; }
+        if (is_mine(own_f) && !tame_wait_smem(&sm.c_done, jf, lane, P.abort_flag)) { alive = false; break; }
         tot_update(sm.ring[jf & RMASK], FalseT{}, 1.0);
+        own_f.next(P.panel, P.world);
     }
     if (!alive) return;            // watchdog: leave the running totals alone, the caller reports TAME_EHANG
     if (c >= 2 && act) {
@@ -844,7 +929,7 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
 #pragma unroll
         for (int x = 0; x < NV; ++x) P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)] = Gc[x];
     }
-    if (FUSED && lane == 0 && (t == 0 || t == T - 1)) {
+    if (FUSED && lane == 0 && (t == 0 || t == P.probe_t)) {
         unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
         dbg[3] = (unsigned long long)wait_unit;
         dbg[4] = (unsigned long long)wait_hand;
@@ -868,8 +953,12 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     const double rdetR = 1.0 / (P.p0 * P.p1 - P.q * P.q);
     const double R00 = P.p1 * rdetR, R11 = P.p0 * rdetR, R01 = -P.q * rdetR;      // R = (R^-1)^-1
     const unsigned long long magic = 0x5AFE000000000000ull + (unsigned long long)(unsigned)P.epoch;
-    auto owned = [&](int k) { return !multi || tame_owned(k, P.panel, P.world, P.rank); };
     auto refresh_at = [&](int k) { return k == i0 || (k % TAME_REFRESH) == 0; };
+    TameOwn own_i, own_n;                                        // nodes i and i+1
+    own_i.init(i0, P.panel, P.world);
+    own_n.init(i0, P.panel, P.world);
+    own_n.next(P.panel, P.world);
+    auto is_mine = [&](const TameOwn& o) { return !multi || o.pw == P.rank; };
     // component c of x = [a,b,U,V] sits at zpos in z = [V,U]; its h entry takes w0 (U rows) or w1 (V rows)
     const int zc = (cc >= 2) ? cc - 2 : 0;                       // index of this lane's component in h[2:], H, hin, ring rows
     const int zpos = (zc < R) ? zc + R : zc - R;                 // where its own new value goes in a ring row
@@ -881,7 +970,7 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     double cw[D];            // raw inverse, column (= row) c; after a down-date it is B_{i+1}^-1
 #pragma unroll
     for (int k = 0; k < D; ++k) cw[k] = 0.0;
-    const bool probe = FUSED && lane == 0 && (t == 0 || t == T - 1);     // timing probes (dbg[0..7]: t=0, [8..15]: t=T-1)
+    const bool probe = FUSED && lane == 0 && (t == 0 || t == P.probe_t);     // timing probes (dbg[0..7]: t=0, [8..15]: t=probe_t)
     unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
     long long wait_in = 0;
     int ncell = 0;
@@ -890,10 +979,10 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     const size_t nstride = (size_t)T * D;
     size_t xoff = ((size_t)i0 * T + t) * D + cc;
 
-    for (int i = i0; i < i1; ++i, xoff += nstride) {
-        if (!owned(i)) continue;
+    for (int i = i0; i < i1; ++i, xoff += nstride, own_i.next(P.panel, P.world), own_n.next(P.panel, P.world)) {
+        if (!is_mine(own_i)) continue;
         const bool refresh = refresh_at(i);
-        const bool do_down = (i + 1 < i1) && owned(i + 1) && !refresh_at(i + 1);
+        const bool do_down = (i + 1 < i1) && is_mine(own_n) && !refresh_at(i + 1);
         {
             const long long c0 = clock64();
             if (!tame_wait_smem(&sm.h_ready, do_down ? i + 1 : i, lane, P.abort_flag)) return;
@@ -988,9 +1077,14 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
                     }
                 }
                 if (c >= 2) sm.ring[i & RMASK][zpos] = mnew;
+                {   // the next time step's helper, if it lives in this CTA, takes the mean from here
+                    const unsigned long long rtag = (unsigned long long)__double_as_longlong(mnew) ^
+                                                    (magic + (unsigned long long)(unsigned)i * 0x9E3779B97F4A7C15ull);
+                    sm.mring[i & (TAME_MR - 1)][c] = make_double2(mnew, __longlong_as_double((long long)rtag));
+                }
                 // raw covariance column -> global scratch; k_covblend applies mask / symmetrisation / jitter / damping
                 // (naive: only the diagonal 1 / (diag(P) + 1e-8) is kept, naive_mf.py:271-274)
-                const int l = (P.world == 1) ? i : tame_lrow(i, P.panel, P.world);
+                const int l = own_i.lrow(P.panel);
                 double* cr = P.Craw + ((size_t)l * T + t) * (D * D) + c;
                 if (mode != 0) {
 #pragma unroll
@@ -1029,6 +1123,10 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
             __threadfence();
             __syncwarp();
             if (lane == 0) tame_st_release(P.progress + t, i + 1);
+            if (FUSED && P.trace != nullptr && lane == 0 && t < 16) {      // when time step t released sub-block i / 32
+                const int nsb = (P.n + TAME_SB - 1) / TAME_SB;
+                P.trace[6 * nsb + 16 * (i / TAME_SB) + t] = tame_globaltimer();
+            }
         }
     }
     if (probe) {
@@ -1052,7 +1150,7 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
     if (wpair >= TAME_CHAIN_WPC) return;
     const int t = cta * TAME_CHAIN_WPC + wpair;
     if (t >= P.T) return;
-    if (is_helper) tame_chain_helper<R, FUSED>(P, warps[wpair], lane, t, i0, i1);
+    if (is_helper) tame_chain_helper<R, FUSED>(P, warps[wpair], (wpair > 0) ? &warps[wpair - 1] : nullptr, lane, t, i0, i1);
     else tame_chain_warp<R, FUSED>(P, warps[wpair], lane, t, i0, i1);
 }
 
@@ -1115,6 +1213,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
     }
     constexpr int NV = 2 * R, JC = TameStream<R, RW>::JC;
     __shared__ int s_val;
+    __shared__ int s_dg[TAME_NG], s_plan[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nslices = (P.T + 31) / 32, nsb = (P.nloc + TAME_SB - 1) / TAME_SB, nunits = nsb * nslices * P.nparts;   // local sub-blocks
     for (;;) {
@@ -1142,6 +1241,9 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
             rv[rr] = (k < P.n) && tv;
             yrow[rr] = P.Y + ((size_t)tame_lrow(min(k, P.n - 1), P.panel, P.world) * P.n * P.T + (tv ? t : 0)) * 2;
         }
+        // optional trace of the unit (sub-block, slice 0, part 0): claim, upper part done, group 0 urgent, group 0 stamped
+        unsigned long long* utr = (P.trace != nullptr && slice == 0 && part == 0 && tid == 0) ? P.trace + 2 * nsb + 4 * lsb : nullptr;
+        if (utr) utr[0] = tame_globaltimer();
         // (a) static upper part: this part's share of the columns j > k
         {
             const int ub = ((kbase + 1) / JC) * JC;
@@ -1161,47 +1263,100 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
             tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, start, je, true, accA, accB, P.cursor + part);
             if (start > jb) tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, jb, start, true, accA, accB, P.cursor + part);
         }
-        // (b) lower columns, released by the chain (carried by part 0)
+        // (b) lower columns, released by the chain (carried by part 0).  The unit's 32 time steps are followed as TAME_NG
+        // groups of 8: the chain warps of a slice are skewed by ~2 us per time step, so the first group of a slice reaches
+        // the unit's rows long before the last group has released the final columns.  Far from the diagonal all groups
+        // advance together (one full-width pass per release); a group whose final columns are out goes alone (the other
+        // lanes are masked), writes its part of H and is stamped separately -- its chain warps wait for nothing else.
+        if (utr) utr[1] = tame_globaltimer();
         const int lowend = (part == 0) ? max(0, (sb - 2) * TAME_SB) : 0;
-        int done_cols = 0, spins = 0;
-        bool dead = false;
-        while (done_cols < lowend && !dead) {
+        // CTA-uniform bookkeeping lives in shared memory (the accumulators own the registers): s_dg[g] = columns done by
+        // group g, s_plan = {c0, c1, active mask} of the next pass; `stamped` is a bit mask
+        if (tid < TAME_NG) s_dg[tid] = (t0 + 8 * tid < P.T) ? 0 : lowend;
+        int stamped = 0, spins = 0;
+        __syncthreads();
+        for (;;) {
+            // ---- groups that are complete: write their H rows once, stamp
+            int newly = 0, all_done = 1;
+#pragma unroll
+            for (int g = 0; g < TAME_NG; ++g) {
+                const bool fin = s_dg[g] >= lowend;
+                if (fin && !((stamped >> g) & 1)) newly |= 1 << g;
+                all_done &= fin ? 1 : 0;
+            }
+            if (newly) {
+                if ((newly >> (lane >> 3)) & 1) {
+#pragma unroll
+                    for (int rr = 0; rr < RW; ++rr) {
+                        const int k = kw + rr;
+                        if (k < P.n && tv) {
+                            double* h = P.H + (size_t)part * P.nloc * P.T * NV + ((size_t)tame_lrow(k, P.panel, P.world) * P.T + t) * NV;
+#pragma unroll
+                            for (int a = 0; a < R; ++a) {
+                                __stcg(h + a, accA[rr][a]);
+                                __stcg(h + R + a, accB[rr][a]);
+                            }
+                        }
+                    }
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid < TAME_NG && ((newly >> tid) & 1)) tame_st_release(P.unit_done + (size_t)u * TAME_NG + tid, P.epoch);
+                if (utr && (newly & 1)) utr[3] = tame_globaltimer();
+                stamped |= newly;
+            }
+            if (all_done) break;
+            // ---- what the chain has released per group -> plan of the next pass (thread 0 decides, everybody follows)
             if (warp == 0) {
                 int v = (t0 + lane < P.T) ? tame_ld_acquire(P.progress + t0 + lane) : 0x7fffffff;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+                for (int o = 4; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+                int tg[TAME_NG];
+#pragma unroll
+                for (int g = 0; g < TAME_NG; ++g) tg[g] = min(lowend, (__shfl_sync(0xffffffffu, v, 8 * g) / TAME_SB) * TAME_SB);
                 if (lane == 0) {
                     if (++spins > TAME_SPIN_LIMIT / 8) atomicExch(P.abort_flag, 1);
-                    s_val = *((volatile int*)P.abort_flag) ? -1 : v;
+                    int c0 = -1, c1 = 0, mask = 0;
+                    if (*((volatile int*)P.abort_flag)) c0 = -2;
+                    else {
+#pragma unroll
+                        for (int g = 0; g < TAME_NG; ++g)            // urgent: a group whose final columns are released
+                            if (c0 < 0 && s_dg[g] < lowend && tg[g] >= lowend) { c0 = s_dg[g]; c1 = lowend; }
+                        if (c0 >= 0) {
+#pragma unroll
+                            for (int g = 0; g < TAME_NG; ++g) if (s_dg[g] == c0 && tg[g] >= lowend) mask |= 1 << g;
+                        } else {
+                            // otherwise, of the groups WITH released columns, those furthest behind advance together (a
+                            // worker that is behind finds every group far ahead and makes one full-width pass; a parked
+                            // worker has nothing better to do than to follow each group eagerly, so that a group's final
+                            // pass is one 32-column slab: the chain warps of a launch drift apart until this coupling
+                            // stops them, so that final pass sits on the chain's critical path)
+                            int dmin = 0x7fffffff, tmin = 0x7fffffff;
+#pragma unroll
+                            for (int g = 0; g < TAME_NG; ++g) if (tg[g] > s_dg[g]) dmin = min(dmin, s_dg[g]);
+#pragma unroll
+                            for (int g = 0; g < TAME_NG; ++g) if (tg[g] > s_dg[g] && s_dg[g] == dmin) tmin = min(tmin, tg[g]);
+                            if (dmin != 0x7fffffff) {
+                                c0 = dmin; c1 = tmin;
+#pragma unroll
+                                for (int g = 0; g < TAME_NG; ++g) if (tg[g] > s_dg[g] && s_dg[g] == dmin) mask |= 1 << g;
+                            }
+                        }
+                    }
+                    s_plan[0] = c0; s_plan[1] = c1; s_plan[2] = mask;
+                    if (utr && c1 == lowend && (mask & 1) && c0 >= 0) utr[2] = tame_globaltimer();
                 }
             }
             __syncthreads();
-            const int avail = s_val;
+            const int c0 = s_plan[0], c1 = s_plan[1], mask = s_plan[2];
             __syncthreads();
-            if (avail < 0) { dead = true; break; }
-            const int target = min(lowend, (avail / TAME_SB) * TAME_SB);
-            if (target > done_cols) {
-                tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, done_cols, target, false, accA, accB);
-                done_cols = target;
-            } else {
-                __nanosleep(256);
-            }
+            if (c0 == -2) break;                             // abort: leave without stamping
+            if (c0 < 0) { __nanosleep(128); continue; }
+            const bool lane_on = (mask >> (lane >> 3)) & 1;      // lanes of the other groups copy nothing and add zeros
+            tame_stream_cols<R, RW>(P, smem_raw, yrow, rv, kw, t0, c0, c1, false, accA, accB, nullptr, lane_on);
+            if (tid < TAME_NG && ((mask >> tid) & 1)) s_dg[tid] = c1;
+            __syncthreads();
         }
-#pragma unroll
-        for (int rr = 0; rr < RW; ++rr) {
-            const int k = kw + rr;
-            if (k < P.n && tv) {
-                double* h = P.H + (size_t)part * P.nloc * P.T * NV + ((size_t)tame_lrow(k, P.panel, P.world) * P.T + t) * NV;
-#pragma unroll
-                for (int a = 0; a < R; ++a) {
-                    __stcg(h + a, accA[rr][a]);
-                    __stcg(h + R + a, accB[rr][a]);
-                }
-            }
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) tame_st_release(P.unit_done + u, P.epoch);
     }
 }
 

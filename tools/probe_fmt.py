@@ -2,7 +2,7 @@
 [0] start ns, [1] first inputs ns, [2] end ns, [3] helper unit-wait, [4] helper hand-wait, [5] helper chain-wait,
 [6] cells, [7] chain input-wait; waits in SM cycles)."""
 import json, sys
-d = json.load(open(sys.argv[1])); p = d["chain_probes"]
+d = [json.loads(l) for l in open(sys.argv[1]) if l.startswith("{")][-1]; p = d["chain_probes"]
 def show(name, q):
     start, first, end, wu, wh, wc, nodes, wi = q[:8]
     nodes = max(nodes, 1)
