@@ -8,10 +8,12 @@ i.e. n^2 * T dyad-timesteps.  At N GPUs the SAME problem is node-sharded (strong
 config 4 (n=8192, T=128, r=8; Y = 137.4 GB FP64) when it fits the GPU, else the largest n that does.
 
 Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the
-host-buffer C-ABI entry (tame_fit_host: host Y/state -> device -> fit -> state back), copies inside the timed
-region; `roofline` is the dominant streaming kernel against the measured HBM peak; `cpu_baseline` is the oracle
-port timed on the host cores on a bounded sample.  --impl reference times the CPU port only (the reference is
-pure Python and cannot travel to the GPU box).
+host-buffer C-ABI entry (tame_fit_host: pinned host Y/state -> device -> fit -> state back) at the SAME n, copies
+inside the timed region; `roofline` is the dominant streaming kernel against the measured HBM peak; `cpu_baseline`
+is the oracle port timed on the host cores on a FIXED sample (CPU_SAMPLE_NODES nodes of the workload), the same
+sample `--impl reference` times, so the two arms describe one configuration.  `extra` carries BASELINE configs 3
+(200 sweeps, three reciprocity values) and 5 (512 batched fits).  --impl reference also times the unmodified
+reference (copied to oracle/_ref at build time, when present) on BASELINE config 1.
 """
 import argparse
 import ctypes as C
@@ -35,6 +37,7 @@ HYPER = dict(ar_coefficient=0.8, rho_additive=0.5, rho_multiplicative=0.3, rho_d
 LR = 0.01
 METRIC = "SMF-VI dyad-timesteps/sec (N^2*T per sweep; sweep + ELBO + MSE per step)"
 UNIT = "dyad-timesteps/s"
+CPU_SAMPLE_NODES = 384      # fixed node subsample of the workload timed on the host (cpu_baseline and --impl reference)
 
 
 def parse_shape(s):
@@ -44,13 +47,22 @@ def parse_shape(s):
     return n, T, r
 
 
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("tame_kernels.cuh", "tame_ops.cu"):
+        with open(os.path.join(PKG, "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(n, T, r, kernel="k_sweep"):
-    """DRAM bytes per launch of the sweep kernel from the committed ncu capture (profiles/r01_traffic.json), when the
-    capture was taken at this configuration; None otherwise."""
+    """DRAM bytes per launch of the sweep kernel from the committed ncu capture (profiles/r02_traffic.json).  None
+    unless the capture was taken at this configuration AND from the kernel sources that are in the tree now."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)
-        if (t["n"], t["T"], t["r"]) == (n, T, r):
+        if (t["n"], t["T"], t["r"]) == (n, T, r) and t.get("source_hash") == kernel_source_hash():
             return t[kernel]["dram_bytes"]
     except Exception:
         pass
@@ -153,26 +165,12 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def cpu_arm(shape, steps, warmup, budget_s=20.0):
-    """Oracle port (sweep_fast + ELBO + MSE) on a node-subsample of the workload sized for ~budget_s of CPU work."""
+def cpu_arm(shape, steps, warmup):
+    """Oracle port (sweep_fast + ELBO + MSE, all host threads NumPy/BLAS uses) on the FIXED sample: the first
+    CPU_SAMPLE_NODES nodes' worth of the workload (same T, r, hyper-parameters, distribution)."""
     from oracle import tame_oracle as orc
     n, T, r = shape
-    # cost model: n_s*T cells, each a + b*n_s seconds (fixed NumPy overhead + partner work); calibrate on two sizes
-    def probe(ns):
-        c, Y, Xm, Xc = cpu_sample_problem(ns, min(T, 8), r)
-        t0 = time.perf_counter()
-        orc.sweep_fast(Y, Xm, Xc, c, LR, orc.GOOD)
-        orc.elbo_mse_fast(Y, Xm, Xc, c, orc.GOOD)
-        return (time.perf_counter() - t0) / (ns * min(T, 8))
-    probe(32)
-    c1, c2 = probe(64), probe(256)
-    b = max((c2 - c1) / 192.0, 1e-9)
-    a = max(c1 - 64 * b, 1e-6)
-    per_step_budget = budget_s / max(1, steps + warmup)
-    # solve ns*T*(a + b*ns) = budget
-    disc = a * a + 4 * b * per_step_budget / T
-    n_s = int((-a + disc ** 0.5) / (2 * b))
-    n_s = max(32, min(n, n_s, 2048))
+    n_s = min(n, CPU_SAMPLE_NODES)
     c, Y, Xm, Xc = cpu_sample_problem(n_s, T, r)
     for _ in range(warmup):
         orc.sweep_fast(Y, Xm, Xc, c, LR, orc.GOOD)
@@ -183,25 +181,75 @@ def cpu_arm(shape, steps, warmup, budget_s=20.0):
         orc.elbo_mse_fast(Y, Xm, Xc, c, orc.GOOD)
     dt = time.perf_counter() - t0
     value = (n_s ** 2) * T * steps / dt
-    return value, dt / steps * 1e3, f"oracle port (NumPy, literal Gauss-Seidel order) on a {n_s}-node subsample of the n={n} workload, T={T}, r={r}, {steps} iteration(s)"
+    return value, dt / steps * 1e3, (f"oracle port (NumPy, literal Gauss-Seidel order) on a fixed {n_s}-node sample of the n={n} "
+                                     f"workload, T={T}, r={r}, {steps} iteration(s) after {warmup} warm-up")
+
+
+def reference_python_arm(max_iter=3):
+    """The UNMODIFIED reference (src/models + src/inference copied to oracle/_ref by build()) on BASELINE config 1
+    (demo.py: n=15, T=10, r=2, good SMF, lr 0.01), float64, timed like experiments/utils.py:201-203."""
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "src", "inference")):
+        return {"unavailable": "oracle/_ref/src not present (build() copies it when /root/reference exists)"}
+    import importlib
+    import torch
+    saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, ref_root)
+    old = torch.get_default_dtype()
+    try:
+        torch.set_default_dtype(torch.float64)
+        torch.set_num_threads(1)
+        models = importlib.import_module("src.models")
+        inference = importlib.import_module("src.inference")
+        model = models.TemporalAMEModel(n_nodes=15, n_time=10, latent_dim=2, ar_coefficient=0.8, rho_dyadic=0.5, seed=42)
+        model.generate_data()
+        vi = inference.TemporalAMEStructuredMFVI(model, factorization="good", learning_rate=0.01, seed=42)
+        t0 = time.time()
+        hist = vi.fit(max_iter=max_iter, tolerance=0.0, verbose=False)
+        dt = time.time() - t0
+        return {"value": 15 * 15 * 10 * max_iter / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"unmodified reference (oracle/_ref), config 1 (n=15 T=10 r=2, good SMF, lr 0.01), {max_iter} fit iterations, float64, 1 thread",
+                "seconds": dt, "elbo_last": float(hist["elbo"][-1])}
+    except Exception as e:                      # the reference arm must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        torch.set_default_dtype(old)
+        sys.path.remove(ref_root)
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def config_dict(n, T, r, world, requested_n=None):
+    """The `config` object of the JSON line -- ONE function for both arms, so that they describe the same configuration."""
+    requested_n = n if requested_n is None else requested_n
+    workload = f"good SMF fit iteration, n={n} T={T} r={r}, lr={LR}" + ("" if n == requested_n else f" (n reduced from {requested_n}: HBM)")
+    units = float(n) * n * T
+    par = f"node-sharded x{world} (64-node panels, cyclic" + (")" if world == 1 else (
+        ", panel scheduler + NCCL broadcasts)" if os.environ.get("TAME_SWEEP") == "panel" else ", fused sweep with NVLink peer hand-over)"))
+    return {"workload": workload, "n": n, "T": T, "r": r, "method": "good", "lr": LR, "parallelism": par,
+            "l2": f"inputs larger than L2: each step streams Y twice ({2 * 16.0 * units / world / 1e9:.1f} GB per GPU per step)"}
 
 
 def run_reference(args, shape):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, sample = cpu_arm(shape, args.steps, args.warmup, budget_s=60.0)
+    value, ms, sample = cpu_arm(shape, args.steps, args.warmup)
     n, T, r = shape
     cores = cpu_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"good SMF fit iteration, n={n} T={T} r={r} (BASELINE config), lr={LR}", "n": n, "T": T, "r": r},
+        "dtype": "f64", "data": "synthetic", "config": config_dict(n, T, r, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python/torch-CPU and is not present on the GPU box; this arm times the oracle port of it",
+        "reference_python": reference_python_arm(),
+        "note": ("the reference is pure Python/torch-CPU (5-13 k dyad-timesteps/s): the line's value is its NumPy port on the "
+                 "fixed sample of this workload; `reference_python` is the unmodified reference itself on BASELINE config 1"),
     }
     print(json.dumps(line), flush=True)
 
@@ -290,12 +338,11 @@ def run_ours(args, shape):
     # fit the workload into HBM: Y rows of this rank + state + scratch, keep 6 GB of slack
     free_b, total_b = torch.cuda.mem_get_info(dev)
     def need(nn):
-        return (nn * nn * T * 2 * 8) / world + nn * T * d * d * 8 * 2.2 + nn * T * d * 8 * 4 + 6e9
+        return (nn * nn * T * 2 * 8) / world + nn * T * d * d * 8 * 2.4 + nn * T * d * 8 * 4 + 6e9
     requested_n = n
     while need(n) > free_b and n > 256:
         n -= 256
     c = hyper_constants(n, T, r)
-    workload = f"good SMF fit iteration, n={n} T={T} r={r}, lr={LR}" + ("" if n == requested_n else f" (n reduced from {requested_n}: HBM)")
 
     X = gen_latents(c).to(dev)
     rows = owned_rows(n, 64, world, rank)
@@ -335,6 +382,7 @@ def run_ours(args, shape):
             dist.barrier()
     _lib.check(lib.tame_bind_Y(h, Y.data_ptr()))
     _lib.check(lib.tame_bind_state(h, Xm.data_ptr(), Xc.data_ptr()))
+    y_sym = bool(lib.tame_y_symmetric(h))
     _lib.check(lib.tame_set_timing(h, 1))
     out6 = (C.c_double * 6)()
 
@@ -444,33 +492,62 @@ def run_ours(args, shape):
                                                                        np.max(np.abs(d_cor[ts].cpu().numpy() - o_cor))))
             del xe_h, xt_h
 
-    # ---- e2e through host buffers (single GPU): host Y/state -> tame_fit_host -> state back
+    # ---- N > 1: self-check of the sharded sweep (the GPU test box of the driver has one GPU): one more sweep, then spot
+    # nodes of rank 0 re-derived with the oracle's update_node from "new means below i, old means from i on" + row i of Y
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(lib, _lib, h, c, Y, Xm, Xc, rows, rank, dev)
+
+    # ---- e2e through host buffers (single GPU): pinned host Y/state -> tame_fit_host -> state back, at the SAME n
     e2e = None
     cpu = None
+    extra = None
     if world == 1 and rank == 0 and not args.no_e2e:
         lib.tame_destroy(h)
         h = None
-        n_e = e2e_nodes(n, T)
-        if n_e != n:                      # regenerate the smaller problem on the device
-            del Y, Xm, Xc, X
-            torch.cuda.empty_cache()
-            c_e = hyper_constants(n_e, T, r)
-            X = gen_latents(c_e).to(dev)
-            Y = torch.empty(n_e, n_e, T, 2, dtype=torch.float64, device=dev)
-            _lib.check(lib.tame_generate_Y(n_e, T, r, _lib.dptr(Rflat), X.data_ptr(), C.c_uint64(42), 0, n_e, Y.data_ptr(), stream))
-            Xm, Xc = init_state(n_e, T, d, dev)
-        host = {}
-        for k, v in (("Y", Y), ("Xm", Xm), ("Xc", Xc)):
-            host[k] = torch.empty(v.shape, dtype=torch.float64, pin_memory=True)
-            host[k].copy_(v)
+        host, n_e, why = None, n, None
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        while avail is not None and n_e * n_e * T * 16 * 1.05 + 6e9 > avail and n_e > 256:
+            n_e -= 256
+            why = f"host RAM: {avail / 1e9:.0f} GB available, Y at n={n} needs {n * n * T * 16 / 1e9:.0f} GB pinned"
+        while host is None:
+            if n_e != n:                      # regenerate the smaller problem on the device
+                Y = Xm = Xc = X = None
+                torch.cuda.empty_cache()
+                c_e = hyper_constants(n_e, T, r)
+                X = gen_latents(c_e).to(dev)
+                Y = torch.empty(n_e, n_e, T, 2, dtype=torch.float64, device=dev)
+                _lib.check(lib.tame_generate_Y(n_e, T, r, _lib.dptr(Rflat), X.data_ptr(), C.c_uint64(42), 0, n_e, Y.data_ptr(), stream))
+                Xm, Xc = init_state(n_e, T, d, dev)
+            try:
+                host = {}
+                for k, v in (("Y", Y), ("Xm", Xm), ("Xc", Xc)):
+                    host[k] = torch.empty(v.shape, dtype=torch.float64, pin_memory=True)
+                    host[k].copy_(v)
+            except RuntimeError as e:         # pinning that much memory failed: shrink and say so
+                host = None
+                why = f"pinned allocation failed at n={n_e} ({str(e)[:80]})"
+                n_e = max(256, (int(n_e * 0.8) // 256) * 256)
         torch.cuda.synchronize(dev)
-        del Y, Xm, Xc, X
+        Y = Xm = Xc = X = None
         torch.cuda.empty_cache()
-        e2e = run_e2e(lib, _lib, (n_e, T, r), n, host, args.steps, dev)
+        e2e = run_e2e(lib, _lib, (n_e, T, r), n, host, args.steps, dev, why)
         del host
     if world == 1 and rank == 0:
+        torch.cuda.empty_cache()
+        if not args.no_extra:
+            extra = {}
+            for name, fn in (("config3", extra_config3), ("config5", extra_config5)):
+                try:
+                    extra[name] = fn(lib, _lib, dev)
+                except Exception as e:        # a side measurement must not take the headline down
+                    extra[name] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu:
-            v, msc, sample = cpu_arm((n, T, r), 1, 0, budget_s=15.0)
+            v, msc, sample = cpu_arm((n, T, r), max(1, min(args.steps, 2)), 1)
             cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample}
     if h is not None:
         lib.tame_destroy(h)
@@ -481,13 +558,13 @@ def run_ours(args, shape):
         sweep_kernel_ms = kt[3] if fused else kt[2]
         contract_gbs = 16.0 * units / world / (sweep_kernel_ms * 1e-3) / 1e9 if sweep_kernel_ms > 0 else None
         llmse_gbs = 16.0 * units / world / (kt[4] * 1e-3) / 1e9 if kt[4] > 0 else None
+
         step_gbs = 32.0 * units / world / (ms / args.steps * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (device Philox generator, same distribution as generate_data)",
-            "config": {"workload": workload, "n": n, "T": T, "r": r, "method": "good", "lr": LR, "parallelism": f"node-sharded x{world} (64-node panels, cyclic" + (")" if world == 1 else (", panel scheduler + NCCL broadcasts)" if os.environ.get("TAME_SWEEP") == "panel" else ", fused sweep with NVLink peer hand-over)")),
-                       "l2": f"inputs larger than L2: each step streams Y twice ({2 * 16.0 * units / world / 1e9:.1f} GB per GPU per step)"},
+            "config": config_dict(n, T, r, world, requested_n),
             "roofline": {"kernel": ("k_sweep (persistent fused Gauss-Seidel sweep: streaming CTAs contract Y with the partner means while the chain CTAs walk the nodes)"
                                     if fused else "k_contract (partner contraction of the sweep: static upper part + right-looking pushes, summed over its launches in one step)"),
                          "bound": "hbm", "achieved": contract_gbs, "peak": peak, "unit": "GB/s",
@@ -496,13 +573,24 @@ def run_ours(args, shape):
                          "algorithmic_bytes_per_unit": 16, "units_per_step": units,
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_unit": 32},
                          "kernels_ms_per_step": {"sweep_total": kt[0], "elbo_total": kt[1], "k_contract": kt[2], ("k_sweep" if fused else "k_chain"): kt[3], "k_llmse": kt[4]},
-                         "k_llmse": {"achieved": llmse_gbs, "frac": (llmse_gbs / peak) if llmse_gbs else None}},
+                         "k_llmse": {"achieved": llmse_gbs, "frac": (llmse_gbs / peak) if llmse_gbs else None,
+                                     "algorithmic_bytes_per_unit": 16,
+                                     "streamed_bytes_per_unit": 8 if y_sym else 16,
+                                     "achieved_streamed": (llmse_gbs * (0.5 if y_sym else 1.0)) if llmse_gbs else None,
+                                     "frac_streamed": (llmse_gbs * (0.5 if y_sym else 1.0) / peak) if llmse_gbs else None,
+                                     "note": ("Y verified mirror-consistent at bind: the pass streams the i<j half (8 B per unit); "
+                                              "frac is on the 16 B contract, frac_streamed on the bytes actually read") if y_sym else
+                                             "full pass (16 B per unit)"}},
             "clocks": clocks, "gpu_launches": int(launches), "elbo_trace_tail": elbos[-2:], "chain_probes": probes,
         }
         if align:
             line["align"] = align
         if e2e:
             line["e2e"] = e2e
+        if extra:
+            line["extra"] = extra
+        if parity:
+            line["parity"] = parity
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -510,20 +598,7 @@ def run_ours(args, shape):
         dist.destroy_process_group()
 
 
-def e2e_nodes(n, T):
-    """Node count of the host-buffer run: the host copy of Y (n^2*T*16 B, pinned) must fit host RAM and the PCIe
-    copies must keep the bench within minutes (cap 48 GB)."""
-    import psutil
-    avail = psutil.virtual_memory().available
-    n_e = n
-    while n_e * n_e * T * 16 * 1.15 + 8e9 > avail and n_e > 256:
-        n_e -= 256
-    if n_e * n_e * T * 16 > 48e9:
-        n_e = int((48e9 / (T * 16)) ** 0.5) // 256 * 256
-    return n_e
-
-
-def run_e2e(lib, _lib, shape, n_full, host, steps, dev):
+def run_e2e(lib, _lib, shape, n_full, host, steps, dev, why=None):
     """tame_fit_host with pinned host buffers (host = dict(Y, Xm, Xc) of pinned CPU tensors)."""
     n_e, T, r = shape
     c = hyper_constants(n_e, T, r)
@@ -540,10 +615,134 @@ def run_e2e(lib, _lib, shape, n_full, host, steps, dev):
     out = {"value": units * nd.value / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / nd.value, "d2h_bytes_per_step": d2h / nd.value,
            "seconds": dt, "steps": int(nd.value), "n": n_e,
            "api": "tame_fit_host (C ABI, pinned host buffers; timed region = device alloc + H2D of Y and state + fit + D2H of state)"}
+    out["same_config"] = (n_e == n_full)
     if n_e != n_full:
-        out["note"] = (f"host-buffer run uses n={n_e} (host Y = {n_e * n_e * T * 16 / 1e9:.1f} GB) instead of n={n_full}: "
-                       "bounded host RAM / PCIe time")
+        out["note"] = f"host-buffer run uses n={n_e} (host Y = {n_e * n_e * T * 16 / 1e9:.1f} GB) instead of n={n_full}: {why}"
     return out
+
+
+def multi_gpu_parity(lib, _lib, h, c, Y, Xm, Xc, rows, rank, dev, n_spots=3):
+    """After the timed region at N > 1: snapshot the means, run ONE more sweep on all ranks, and let rank 0 re-derive a
+    few of ITS nodes with the oracle's update_node (structured_mf.py:220-287) from 'new means below i, old means from
+    i on' + row i of Y.  Returns the worst relative errors (rank 0) -- the 1e-9 bar of north_star applies."""
+    import torch
+    from oracle import tame_oracle as orc
+    oc = orc.derived_constants(dict(n=c["n"], T=c["T"], r=c["r"], d=c["d"], R=c["R"], Sigma=c["S0"][:2, :2], Psi=c["S0"][2:, 2:],
+                                   Phi=c["Phi"], Q=c["Q"]))
+    n = c["n"]
+    # spot nodes of rank 0: first node, a sub-block / refresh / panel boundary of its second panel, its last node
+    mine = [i for (a, b) in rows for i in range(a, b)]
+    spots = sorted({mine[0], mine[min(len(mine) - 1, 64)], mine[min(len(mine) - 1, 64 + 33)], mine[-1]})[:max(1, n_spots + 1)]
+    old_m = Xm.cpu().numpy() if rank == 0 else None
+    old_c = {i: Xc[i].cpu().numpy() for i in spots} if rank == 0 else None
+    _lib.check(lib.tame_sweep(h))
+    torch.cuda.synchronize(dev)
+    if rank != 0:
+        return None
+
+    class OneRow:
+        def __init__(self, i, blk): self.i, self.rows = i, blk
+        def __getitem__(self, k): return self.rows[k[1]]
+        def __setitem__(self, k, v): self.rows[k[1]] = v
+    new_m = Xm.cpu().numpy()
+    local_of = {}
+    at = 0
+    for a, b in rows:
+        for i in range(a, b):
+            local_of[i] = at + (i - a)
+        at += b - a
+    wm = wc = 0.0
+    mix = new_m.copy()
+    for i in spots:
+        mix[:i] = new_m[:i]
+        mix[i:] = old_m[i:]
+        row = Y[local_of[i]].cpu().numpy()[None]
+        cov = OneRow(i, old_c[i].copy())
+        orc.update_node(row, mix, cov, i, oc, LR, orc.GOOD, row=0)
+        wm = max(wm, float(np.max(np.abs(mix[i] - new_m[i])) / np.max(np.abs(mix[i]))))
+        wc = max(wc, float(np.max(np.abs(cov.rows - Xc[i].cpu().numpy())) / np.max(np.abs(cov.rows))))
+    return {"mean": wm, "cov": wc, "spot_nodes": spots, "tolerance": 1e-9, "ok": bool(wm < 1e-9 and wc < 1e-9),
+            "how": "one extra sweep after the timed region; oracle update_node on rank 0's spot nodes (new means below i, old from i on)"}
+
+
+def extra_config3(lib, _lib, dev, sweeps=200):
+    """BASELINE config 3: good SMF, n=1024 T=64 r=4, 200 sweeps (fit iterations), reciprocity rho in {0, 0.5, 0.8}."""
+    import torch
+    n, T, r = CONFIGS["3"]
+    d = 2 + 2 * r
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    peak, _ = measured_peak()
+    out = {"workload": f"good SMF, n={n} T={T} r={r}, lr={LR}, {sweeps} fit iterations (sweep + ELBO + MSE), inputs resident", "runs": []}
+    for rho in (0.0, 0.5, 0.8):
+        c = hyper_constants(n, T, r, rho=rho)
+        X = gen_latents(c).to(dev)
+        Y = torch.empty(n, n, T, 2, dtype=torch.float64, device=dev)
+        _lib.check(lib.tame_generate_Y(n, T, r, _lib.dptr(np.ascontiguousarray(c["R"].reshape(4))), X.data_ptr(), C.c_uint64(42), 0, n,
+                                       Y.data_ptr(), stream))
+        Xm, Xc = init_state(n, T, d, dev)
+        cfg, keep = make_cfg(_lib, c, n, T, r, dev.index, 1, 0)
+        h = C.c_void_p()
+        _lib.check(lib.tame_create(C.byref(cfg), C.byref(h)))
+        _lib.check(lib.tame_bind_Y(h, Y.data_ptr()))
+        _lib.check(lib.tame_bind_state(h, Xm.data_ptr(), Xc.data_ptr()))
+        el = np.zeros(sweeps); ms = np.zeros(sweeps); nd = C.c_int32(0)
+        _lib.check(lib.tame_fit(h, 3, 0.0, _lib.dptr(el), _lib.dptr(ms), C.byref(nd)))        # warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.tame_fit(h, sweeps, 0.0, _lib.dptr(el), _lib.dptr(ms), C.byref(nd)))
+        e1.record()
+        torch.cuda.synchronize(dev)
+        per = e0.elapsed_time(e1) / nd.value
+        gbs = 32.0 * n * n * T / (per * 1e-3) / 1e9
+        out["runs"].append({"rho": rho, "ms_per_step": per, "value": float(n) * n * T / (per * 1e-3), "unit": UNIT,
+                            "step_frac_of_hbm_peak": gbs / peak, "elbo_first": float(el[0]), "elbo_last": float(el[nd.value - 1]),
+                            "mse_last": float(ms[nd.value - 1])})
+        lib.tame_destroy(h)
+        del Y, X, Xm, Xc
+    return out
+
+
+def extra_config5(lib, _lib, dev, max_iter=150, tolerance=1e-4):
+    """BASELINE config 5: 512 independent fits (n x T x ar x rho grid, r=2, naive + good) through tame_fit_batch."""
+    import torch
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    r = 2
+    d = 2 + 2 * r
+    ns, Ts, ars, rhos = [10, 20, 32, 50, 64, 100, 160, 256], [5, 10, 20, 40], [0.5, 0.9], [0.0, 0.3, 0.6, 0.8]
+    problems = [(n, T, ar, rho) for n in ns for T in Ts for ar in ars for rho in rhos]
+    nf = 2 * len(problems)
+    cfgs = (_lib.TameConfig * nf)()
+    Yp, Mp, Cp = (C.c_void_p * nf)(), (C.c_void_p * nf)(), (C.c_void_p * nf)()
+    keep, f = [], 0
+    for k, (n, T, ar, rho) in enumerate(problems):
+        c = hyper_constants(n, T, r, ar=ar, rho=rho)
+        X = gen_latents(c, seed=100 + k).to(dev)
+        Y = torch.empty(n, n, T, 2, dtype=torch.float64, device=dev)
+        _lib.check(lib.tame_generate_Y(n, T, r, _lib.dptr(np.ascontiguousarray(c["R"].reshape(4))), X.data_ptr(), C.c_uint64(100 + k), 0, n,
+                                       Y.data_ptr(), stream))
+        for mode in (_lib.MODE_NAIVE, _lib.MODE_GOOD):
+            Xm, Xc = init_state(n, T, d, dev, seed=7 + k)
+            cfg, kk = make_cfg(_lib, c, n, T, r, dev.index, 1, 0)
+            cfg.mode = mode
+            cfgs[f] = cfg
+            keep.append((kk, Y, Xm, Xc))
+            Yp[f], Mp[f], Cp[f] = Y.data_ptr(), Xm.data_ptr(), Xc.data_ptr()
+            f += 1
+    torch.cuda.synchronize(dev)
+    el = np.zeros((nf, max_iter)); ms = np.zeros((nf, max_iter)); nd = (C.c_int32 * nf)()
+    launches0 = lib.tame_launch_count()
+    t0 = time.time()
+    _lib.check(lib.tame_fit_batch(nf, cfgs, Yp, Mp, Cp, max_iter, tolerance, _lib.dptr(el), _lib.dptr(ms), nd, 0))
+    torch.cuda.synchronize(dev)
+    sec = time.time() - t0
+    iters = np.array(list(nd), dtype=np.int64)
+    units = sum(float(n) * n * T * float(it2.sum()) for (n, T, ar, rho), it2 in zip(problems, iters.reshape(-1, 2)))
+    return {"workload": f"{nf} independent fits (n in {ns}, T in {Ts}, ar in {ars}, rho in {rhos}, r=2, naive + good), max_iter {max_iter}, "
+                        f"tolerance {tolerance}, lr {LR}; inputs resident, traces to the host",
+            "seconds": sec, "fits_per_s": nf / sec, "iterations_total": int(iters.sum()), "value": units / sec, "unit": UNIT,
+            "early_stopped": int((iters < max_iter).sum()), "gpu_launches": int(lib.tame_launch_count() - launches0),
+            "finite": bool(np.all(np.isfinite(el[np.arange(nf), iters - 1])))}
+
 
 
 def main():
@@ -555,6 +754,7 @@ def main():
     ap.add_argument("--config", default="4", help="4 (default), 3, 2, 1 or n,T,r")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-5 side measurements")
     args = ap.parse_args()
     shape = parse_shape(args.config)
     if args.impl == "reference":

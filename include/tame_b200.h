@@ -186,6 +186,9 @@ int tame_ipc_import(tame_handle* h, const void* handles_host);
 /* all-gather the X_cov rows (X_mean is already replicated) so every rank holds the full state */
 int tame_gather_state(tame_handle* h);
 
+/* 1 when tame_bind_Y verified Y[j,i,t,:] == swap(Y[i,j,t,:]) bit for bit (the ELBO pass then streams the i<j half), else 0 */
+int tame_y_symmetric(const tame_handle* h);
+
 /* ---- diagnostics ----------------------------------------------------------------------------------------- */
 /* device time of the last tame_sweep / tame_elbo_mse in milliseconds, measured with CUDA events on the
  * handle's stream; *_kernel_ms of the dominant kernel(s) inside it. */

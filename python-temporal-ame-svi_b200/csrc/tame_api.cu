@@ -482,6 +482,8 @@ int tame_set_stream(tame_handle* h, void* s) {
     return TAME_OK;
 }
 
+int tame_y_symmetric(const tame_handle* h) { return (h && h->y_symmetric) ? 1 : 0; }
+
 int tame_local_rows(const tame_handle* h, int32_t* out) {
     if (!h || !out) return fail(TAME_EINVAL, "null argument");
     *out = h->nloc;

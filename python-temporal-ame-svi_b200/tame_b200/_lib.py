@@ -67,6 +67,7 @@ SIGNATURES = {
     "tame_gather_state": (C.c_int, [_P]),
     "tame_last_timing": (C.c_int, [_P, _DP, _DP, _DP, _DP, _DP]),
     "tame_set_timing": (C.c_int, [_P, C.c_int32]),
+    "tame_y_symmetric": (C.c_int, [_P]),
     "tame_debug_probes": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "tame_debug_trace": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32]),
 }
