@@ -196,7 +196,7 @@ int tame_last_timing(tame_handle* h, double* sweep_ms, double* elbo_ms, double* 
                      double* llmse_ms);
 int tame_set_timing(tame_handle* h, int32_t enabled);
 /* timing probes of the last fused sweep (k_sweep): [0..7] the warp pair of time step 0, [8..15] of time step T-1:
- * {start ns, first inputs ns, end ns, helper cycles waiting for streaming units, for the hand-over of (i,t-1), for
+ * {start ns, chain-warp cycles waiting for the NEXT node's inputs, end ns, helper cycles waiting for streaming units, for the hand-over of (i,t-1), for
  *  the chain warp, cells done, chain-warp cycles waiting for its inputs} */
 int tame_debug_probes(tame_handle* h, uint64_t* out16_host);
 /* with TAME_TRACE=1 in the environment at tame_create: per 32-node sub-block, the globaltimer stamps (ns) at which the

@@ -437,7 +437,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
         const char* v = getenv("TAME_SWEEP");   // "panel" forces the stream-ordered per-panel path (debug / comparison)
         h->fused = (world == 1) && !(v && strcmp(v, "panel") == 0);
         h->fused_multi = !(v && strcmp(v, "panel") == 0);
-        if (h->fused && (T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC + 1 > h->ops->sweep_capacity()) h->fused = false;
+        if (h->fused && (T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC + 1 > h->ops->sweep_capacity(1)) h->fused = false;
     }
 
     TameParams& P = h->P;

@@ -442,48 +442,64 @@ __device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rowb
 // symmetrisation, the jitter and the damped write into X_cov happen in a streaming post-pass (k_covblend).
 // Mailboxes (shared memory):  helper -> chain  inp[k] {h without the last TAME_NL partners, old mean, those partners'
 // weights, diag(P)} + the precision column at refresh nodes (pcol);  chain -> helper  ring[k] (new z).
-// Counters h_ready / c_done.
+// Counters: ready[slot] (inputs of the node in that mailbox slot), t_ready (totals-side data), f_done (foreign nodes),
+// c_done (chain).
+// Two shapes of the warp team per time step (template NH):
+//   NH = 1  chain warp + ONE helper that does everything above; 4 time steps per CTA (streaming-bound problems: the
+//           chain CTAs take few SMs)
+//   NH = 2  chain warp + a TOTALS warp (running moments, precision column at refresh nodes, diag(P), foreign nodes) + TWO
+//           INPUT warps that prepare alternate nodes; 2 time steps per CTA (chain-bound problems: small n, multi-GPU)
 // ------------------------------------------------------------------------------------------------------
-#define TAME_NL 2            // trailing partners (i-NL..i-1) whose terms the chain warp adds itself: the helper runs NL nodes ahead
-#define TAME_LA 4            // look-ahead of the helper's global loads, in nodes
-#define TAME_NSLOT 8         // depth of the staging ring (power of two, >= TAME_LA + 2)
-#define TAME_NINP 4          // depth of the helper -> chain mailbox (power of two, >= TAME_NL + 2)
+#define TAME_NL 3            // trailing partners (i-NL..i-1) whose terms the chain warp adds itself: the helpers run NL nodes ahead
+#define TAME_LA 4            // look-ahead of a helper's global loads, in its own loop iterations (NH = 1)
+#define TAME_LA2 3           // same for the input warps of NH = 2 (an iteration is two nodes there)
+#define TAME_NINP 8          // depth of the helper -> chain mailbox (power of two, >= TAME_NL + 2)
 #define TAME_MR 16           // depth of the intra-CTA hand-over ring (self-validating slots; the global slot is the fallback)
 #define TAME_WMAX 96         // widest inline window (partners)
 #define TAME_WATCHDOG_NS 4000000000ull
+enum { TAME_ROLE_ALL = 0, TAME_ROLE_TOTALS = 1, TAME_ROLE_INPUT = 2 };
 
-template <int R>
+template <int R, int NH>
 struct __align__(16) TameChainSmem {
     static constexpr int D = 2 + 2 * R, NV = 2 * R, TOT = TameTot<R>::TOT, DP = D + 1;
+    static constexpr int NSLOT = (NH == 1) ? 8 : 16;   // staging ring of the input side (power of two)
+    static constexpr int NTS = (NH == 1) ? 1 : 8;      // staging ring of the totals warp (NH = 2)
     struct Stage {                                  // one node's global inputs (cp.async destinations, 16-byte aligned)
         double2 ywin[TAME_WMAX];                    // Y[i, wlo + s, t, :] of the inline window
-        double2 hand[D];                            // hand-over slot {new mean, tag} of (i, t-1); foreign nodes: of (i, t)
+        double2 hand[D];                            // hand-over slot {new mean, tag} of (i, t-1); foreign nodes (NH = 1): of (i, t)
         double mold[D], mnext[D];                   // old means of (i,t) and (i,t+1)
         double H[TAME_MAX_PARTS][NV];               // static partner part (per column part)
         double hab[2];
+    };
+    struct TStage {                                 // the totals warp's own staging (NH = 2)
+        double2 hand[D];                            // foreign nodes: hand-over slot of (i, t)
+        double mold[D];
     };
     struct Inp {                                    // helper -> chain
         double hrest[D];                            // h of the cell without the trailing partners' terms
         double mold[D];
         double wl[TAME_NL][2];                      // (w0, w1) of the trailing partners: wl[q] <-> partner i-1-q
-        double pdiag[D];                            // diag(P) without the trailing partners (naive rule)
     };
     double ring[TAME_RING][NV];                     // z = [V,U] (new) of the last TAME_RING nodes at this time step
-    Stage st[TAME_NSLOT];
-    double pcol[D * DP];                            // helper -> chain at refresh nodes: the precision without the trailing partners
+    Stage st[NSLOT];
+    TStage tst[NTS];
+    double pcol[D * DP];                            // totals side -> chain at refresh nodes: the precision without the trailing partners
+    double pdt[TAME_NINP][D];                       // totals side -> chain: diag(P) without the trailing partners (naive rule)
     Inp inp[TAME_NINP];
-    double2 wbuf[TAME_WMAX];                        // (w0, w1) of the window
+    double2 wbuf[NH][TAME_WMAX];                    // (w0, w1) of the window, per input warp
     double2 Fs[2][32];                              // F = M J' of the up-date / down-date, one row per lane
     double rowb[TAME_GJ_ROWB(D)];
-    double hvec[D], mprev[D], hin[NV];
+    double hvec[D], mprev[NH][D], hin[NH][NV];
     double2 mring[TAME_MR][D];                      // chain -> helper of the next time step in the same CTA: {new mean, tag}
-    int h_ready;                                    // last node whose inputs the helper has published
+    int ready[TAME_NINP];                           // node whose inputs sit in mailbox slot s
+    int t_ready;                                    // last node whose totals-side data (pcol, pdt) is published
+    int f_done;                                     // last foreign node taken over (X_mean replica, ring)
     int c_done;                                     // last node the chain warp has finished
-    int pad_[2];
+    int pad_;
 };
-static_assert(sizeof(TameChainSmem<1>) % 16 == 0 && sizeof(TameChainSmem<2>) % 16 == 0 && sizeof(TameChainSmem<3>) % 16 == 0 &&
-              sizeof(TameChainSmem<4>) % 16 == 0 && sizeof(TameChainSmem<8>) % 16 == 0, "per-warp chain block must stay 16-byte aligned");
-static_assert(TAME_LA + 2 <= TAME_NSLOT && TAME_NL + 2 <= TAME_NINP, "mailbox depth");
+static_assert(sizeof(TameChainSmem<1, 1>) % 16 == 0 && sizeof(TameChainSmem<2, 1>) % 16 == 0 && sizeof(TameChainSmem<3, 1>) % 16 == 0 &&
+              sizeof(TameChainSmem<4, 2>) % 16 == 0 && sizeof(TameChainSmem<8, 2>) % 16 == 0, "per-time-step chain block must stay 16-byte aligned");
+static_assert(TAME_LA + 2 <= 8 && 2 * (TAME_LA2 + 1) + 4 <= 16 && TAME_NL + 2 <= TAME_NINP, "mailbox depth");
 
 // panel-cyclic ownership of consecutive nodes without integer divisions: rem = k % panel, pw = (k / panel) % world,
 // lb = (k / panel) / world; owned = (pw == rank), local row = lb * panel + rem
@@ -567,15 +583,19 @@ __device__ __forceinline__ void tame_rank2_apply(double (&cw)[2 + 2 * R], const 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// helper warp of time step t
+// helper warp(s) of time step t.  ROLE_ALL: the one helper of NH = 1.  ROLE_TOTALS / ROLE_INPUT (hi = 0,1): the team of NH = 2;
+// an input warp takes the nodes i0 + hi, i0 + hi + 2, ...
 // ------------------------------------------------------------------------------------------------------
-template <int R, bool FUSED>
-__device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChainSmem<R>& sm, const TameChainSmem<R>* pv, int lane, int t,
-                                                  int i0, int i1) {
-    using S = TameChainSmem<R>;
+template <int R, bool FUSED, int NH, int ROLE>
+__device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChainSmem<R, NH>& sm, const TameChainSmem<R, NH>* pv, int lane,
+                                                  int t, int hi, int i0, int i1) {
+    using S = TameChainSmem<R, NH>;
+    constexpr bool DO_TOT = (ROLE != TAME_ROLE_INPUT), DO_INP = (ROLE != TAME_ROLE_TOTALS);
+    constexpr int STEP = (ROLE == TAME_ROLE_INPUT) ? NH : 1;
     constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP;
     constexpr int WSB = FUSED ? TAME_SB : TAME_WIN, WBACK = FUSED ? 2 : 0, NWS = FUSED ? 3 : 2;
-    constexpr int NL = TAME_NL, LA = TAME_LA, SMASK = TAME_NSLOT - 1, IMASK = TAME_NINP - 1, RMASK = TAME_RING - 1;
+    constexpr int NL = TAME_NL, LA = (NH == 1) ? TAME_LA : ((ROLE == TAME_ROLE_INPUT) ? TAME_LA2 : TAME_LA);
+    constexpr int SMASK = (DO_INP ? S::NSLOT : S::NTS) - 1, IMASK = TAME_NINP - 1, RMASK = TAME_RING - 1;
     const int T = P.T, c = lane, cc = min(c, D - 1);
     const bool act = c < D, has_prev = t > 0, has_next = t < T - 1;
     const bool multi = FUSED && P.npeers > 0;
@@ -595,46 +615,58 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
         return ((unsigned long long)__double_as_longlong(v.x) ^ (unsigned long long)__double_as_longlong(v.y)) ==
                magic + (unsigned long long)(unsigned)k * 0x9E3779B97F4A7C15ull;
     };
-    // ownership of the three node streams this warp walks: k (current), k-1-NL (folded into the totals), k+1+LA (staged)
+    // ownership of the node streams this warp walks: k (current), k-1-NL (its ring row must be there), the staged node
+    const int kfirst = i0 + ((ROLE == TAME_ROLE_INPUT) ? hi : 0);
     TameOwn own_k, own_f, own_s;
-    own_k.init(i0, P.panel, P.world);
+    own_k.init(min(kfirst, P.n - 1), P.panel, P.world);
     own_f.init(i0, P.panel, P.world);
-    own_s.init(i0, P.panel, P.world);
+    own_s = own_k;
+    int f_at = i0;                                                    // node own_f stands at
     auto is_mine = [&](const TameOwn& o) { return !multi || o.pw == P.rank; };
+    auto own_step = [&](TameOwn& o) {
+#pragma unroll
+        for (int q = 0; q < STEP; ++q) o.next(P.panel, P.world);
+    };
 
     // rows cc of Qinv Phi and Phi' Qinv (AR(1) terms of h, structured_mf.py:258,264) and the constant part of diag(P)
-    double qp[D], pq[D];
+    double qp[DO_INP ? D : 1], pq[DO_INP ? D : 1];
+    if (DO_INP) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        qp[k] = P.cst[3 * D * D + cc * D + k];
-        pq[k] = P.cst[4 * D * D + cc * D + k];
+        for (int k = 0; k < D; ++k) {
+            qp[k] = P.cst[3 * D * D + cc * D + k];
+            pq[k] = P.cst[4 * D * D + cc * D + k];
+        }
     }
     const double cdiag = (has_prev ? P.cst[1 * D * D + cc * D + cc] : P.cst[cc * D + cc]) + (has_next ? P.cst[2 * D * D + cc * D + cc] : 0.0);
     // running partner moments of this time step: lane c >= 2 owns column y = c-2 of G = sum_j z_j z_j' (and g[y], G[y][y]);
     // lanes 0,1 hold g = sum_j z_j -- exactly what the lane needs to form its column of the observation precision
-    double Gc[NV], gy = 0.0, gd = 0.0;
+    double Gc[DO_TOT ? NV : 1], gy = 0.0, gd = 0.0;
+    if (DO_TOT) {
 #pragma unroll
-    for (int x = 0; x < NV; ++x) {
-        double v = 0.0;
-        if (c < 2) v = P.tot[(size_t)t * TOT + x];
-        else if (act) v = P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)];
-        Gc[x] = v;
-    }
-    if (c >= 2 && act) {
-        gy = P.tot[(size_t)t * TOT + (c - 2)];
-        gd = P.tot[(size_t)t * TOT + NV + (c - 2) * NV + (c - 2)];
+        for (int x = 0; x < NV; ++x) {
+            double v = 0.0;
+            if (c < 2) v = P.tot[(size_t)t * TOT + x];
+            else if (act) v = P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)];
+            Gc[x] = v;
+        }
+        if (c >= 2 && act) {
+            gy = P.tot[(size_t)t * TOT + (c - 2)];
+            gd = P.tot[(size_t)t * TOT + NV + (c - 2) * NV + (c - 2)];
+        }
     }
     // tot += sign * (z, z z'); z read from shared memory in z order (ring row) or from a mean vector in x order
     using TrueT = std::true_type;
     using FalseT = std::false_type;
     auto tot_update = [&](const double* m, auto xorder, double sign) {
         constexpr bool XO = decltype(xorder)::value;
-        double zy = 0.0;
-        if (c < 2) zy = sign;
-        else if (act) zy = sign * m[XO ? tame_zidx<R>(c - 2) : c - 2];
+        if (DO_TOT) {
+            double zy = 0.0;
+            if (c < 2) zy = sign;
+            else if (act) zy = sign * m[XO ? tame_zidx<R>(c - 2) : c - 2];
 #pragma unroll
-        for (int x = 0; x < NV; ++x) Gc[x] = fma(m[XO ? tame_zidx<R>(x) : x], zy, Gc[x]);
-        if (c >= 2) { gy += zy; gd = fma(zy * zy, sign, gd); }
+            for (int x = 0; x < (DO_TOT ? NV : 1); ++x) Gc[x] = fma(m[XO ? tame_zidx<R>(x) : x], zy, Gc[x]);
+            if (c >= 2) { gy += zy; gd = fma(zy * zy, sign, gd); }
+        }
     };
     double sA, sB;   // scale pattern of P_obs: rows x<R of the z-block use sA, rows x>=R use sB
     if (c == 0) { sA = P.p0; sB = P.q; }
@@ -645,17 +677,26 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
     long long wait_unit = 0, wait_hand = 0, wait_chain = 0;
     bool alive = true;
 
-    // stage ALL global inputs of node k (cp.async; the caller commits one group per loop iteration).  At the first node of a
-    // sub-block the stamp of its streaming unit (static partner part H) is awaited first.
+    // stage the global inputs of node k this role needs (cp.async; the caller commits one group per loop iteration).  At
+    // the first node of a sub-block the stamp of its streaming unit (static partner part H) is awaited first.
     auto stage = [&](int k, bool mine_s, int l) {
-        typename S::Stage& s = sm.st[k & SMASK];
         const size_t cell = (size_t)k * T + t;
         const double* xm = P.Xm + cell * D;
-        if (lane < D / 2) tame_cp_async16(&s.mold[2 * lane], xm + 2 * lane, true);
-        if (!mine_s) {
-            if (act) tame_cp_async16(&s.hand[c], hand_mine + (size_t)k * T * D, true);
+        if (!DO_INP) {                                          // totals warp: old mean of every node, hand-over slot of foreign ones
+            typename S::TStage& s = sm.tst[k & SMASK];
+            if (lane < D / 2) tame_cp_async16(&s.mold[2 * lane], xm + 2 * lane, true);
+            if (!mine_s && act) tame_cp_async16(&s.hand[c], hand_mine + (size_t)k * T * D, true);
             return;
         }
+        typename S::Stage& s = sm.st[k & SMASK];
+        if (!mine_s) {
+            if (DO_TOT) {
+                if (lane < D / 2) tame_cp_async16(&s.mold[2 * lane], xm + 2 * lane, true);
+                if (act) tame_cp_async16(&s.hand[c], hand_mine + (size_t)k * T * D, true);
+            }
+            return;
+        }
+        if (lane < D / 2) tame_cp_async16(&s.mold[2 * lane], xm + 2 * lane, true);
         if (has_prev && act) tame_cp_async16(&s.hand[c], hand_prev + (size_t)k * T * D, true);
         if (has_next && lane >= 16 && lane < 16 + D / 2) tame_cp_async16(&s.mnext[2 * (lane - 16)], xm + D + 2 * (lane - 16), true);
         const int wlo = window_lo(k);
@@ -665,9 +706,9 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
             const int sl = lane + 32 * u;
             if (wlo + sl < k) tame_cp_async16(&s.ywin[sl], yb + (size_t)sl * T * 2, true);
         }
-        if (FUSED && (k % TAME_SB) == 0) {
+        if (FUSED && ((k % TAME_SB) < STEP)) {                   // this warp's first node of the sub-block
             const long long c0 = clock64();
-            if (P.trace != nullptr && t == 0 && lane == 0) P.trace[2 * (k / TAME_SB)] = tame_globaltimer();
+            if (P.trace != nullptr && t == 0 && lane == 0 && (k % TAME_SB) == 0) P.trace[2 * (k / TAME_SB)] = tame_globaltimer();
             int ok = 1;
             if (lane == 0) {
                 const int* flag = P.unit_done + (size_t)((l / TAME_SB) * nslices + (t >> 5)) * P.nparts * TAME_NG + ((t >> 3) & (TAME_NG - 1));
@@ -679,7 +720,7 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
             ok = __shfl_sync(0xffffffffu, ok, 0);
             __syncwarp();
             wait_unit += clock64() - c0;
-            if (P.trace != nullptr && t == 0 && lane == 0) P.trace[2 * (k / TAME_SB) + 1] = tame_globaltimer();
+            if (P.trace != nullptr && t == 0 && lane == 0 && (k % TAME_SB) == 0) P.trace[2 * (k / TAME_SB) + 1] = tame_globaltimer();
             if (!ok) { alive = false; return; }
         }
         const size_t lcell = (size_t)l * T + t;
@@ -690,214 +731,234 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
         }
     };
 
-    for (int u = 0; u <= LA; ++u) {
-        if (alive && i0 + u < i1) stage(i0 + u, is_mine(own_s), own_s.lrow(P.panel));
-        own_s.next(P.panel, P.world);
-        tame_cp_async_commit();
+    {
+        int ks = kfirst;
+        for (int u = 0; u <= LA; ++u, ks += STEP) {
+            if (alive && ks < i1) stage(ks, is_mine(own_s), own_s.lrow(P.panel));
+            own_step(own_s);
+            tame_cp_async_commit();
+        }
     }
-    for (int k = i0; k < i1 && alive; ++k) {
+    for (int k = kfirst; k < i1 && alive; k += STEP) {
         const bool mine = is_mine(own_k);
         tame_cp_async_wait<LA>();
         __syncwarp();
-        const typename S::Stage& s = sm.st[k & SMASK];
 
-        // ---- totals: node k-1-NL enters with its new mean (its z is in the ring), node k leaves with its old mean
+        // ---- the ring must hold every node up to k-1-NL (chain: its own nodes, totals side: foreign nodes); the totals
+        // side folds them into the running moments as it passes: node k-1-NL enters with its new mean, node k leaves
+        // with its old one
         const int jf = k - 1 - NL;
         if (jf >= i0) {
+            while (f_at < jf) { own_f.next(P.panel, P.world); ++f_at; }
+            const long long c0 = clock64();
             if (is_mine(own_f)) {
-                const long long c0 = clock64();
                 if (!tame_wait_smem(&sm.c_done, jf, lane, P.abort_flag)) { alive = false; break; }
-                wait_chain += clock64() - c0;
+            } else if (!DO_TOT) {
+                if (!tame_wait_smem(&sm.f_done, jf, lane, P.abort_flag)) { alive = false; break; }
             }
+            wait_chain += clock64() - c0;
             tot_update(sm.ring[jf & RMASK], FalseT{}, 1.0);
-            own_f.next(P.panel, P.world);
         }
-        tot_update(s.mold, TrueT{}, -1.0);
+        if (DO_TOT) tot_update(DO_INP ? sm.st[k & SMASK].mold : sm.tst[k & SMASK].mold, TrueT{}, -1.0);
 
         if (!mine) {
-            // ---- node of another rank: its owner wrote {new mean, tag} straight into this rank's hand-over slots over
-            // NVLink; keep the replicated X_mean, the window ring and the progress counter in step
-            double2 hf = s.hand[cc];
-            TameSpin sp;
-            for (;;) {
-                if (__all_sync(0xffffffffu, !act || tag_ok(hf))) break;
-                int ex = 0;
-                if (lane == 0) ex = sp.expired(P.abort_flag) ? 1 : 0;
-                if (__shfl_sync(0xffffffffu, ex, 0)) { alive = false; break; }
-                if (act) hf = tame_ld_volatile2(hand_mine + (size_t)k * T * D);
-            }
-            if (!alive) break;
-            if (act) {
-                tame_st_cg(P.Xm + ((size_t)k * T + t) * D + c, hf.x);
-                if (c >= 2) sm.ring[k & RMASK][(c - 2 < R) ? c - 2 + R : c - 2 - R] = hf.x;
-            }
-            if (((k + 1) % TAME_SB) == 0 || k + 1 == i1) {
-                __threadfence();
+            if (DO_TOT) {
+                // ---- node of another rank: its owner wrote {new mean, tag} straight into this rank's hand-over slots over
+                // NVLink; keep the replicated X_mean, the window ring and the progress counter in step
+                double2 hf = DO_INP ? sm.st[k & SMASK].hand[cc] : sm.tst[k & SMASK].hand[cc];
+                TameSpin sp;
+                for (;;) {
+                    if (__all_sync(0xffffffffu, !act || tag_ok(hf))) break;
+                    int ex = 0;
+                    if (lane == 0) ex = sp.expired(P.abort_flag) ? 1 : 0;
+                    if (__shfl_sync(0xffffffffu, ex, 0)) { alive = false; break; }
+                    if (act) hf = tame_ld_volatile2(hand_mine + (size_t)k * T * D);
+                }
+                if (!alive) break;
+                if (act) {
+                    tame_st_cg(P.Xm + ((size_t)k * T + t) * D + c, hf.x);
+                    if (c >= 2) sm.ring[k & RMASK][(c - 2 < R) ? c - 2 + R : c - 2 - R] = hf.x;
+                }
+                if (((k + 1) % TAME_SB) == 0 || k + 1 == i1) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) tame_st_release(P.progress + t, k + 1);
+                }
+                __threadfence_block();
                 __syncwarp();
-                if (lane == 0) tame_st_release(P.progress + t, k + 1);
+                if (lane == 0) *((volatile int*)&sm.f_done) = k;
             }
         } else {
-            // ---- the window's weights  w0 = p0 y0 + q y1, w1 = q y0 + p1 y1  (structured_mf.py:324)
-            const int wlo = window_lo(k), nle = min(NL, k - i0), cnt = (k - nle) - wlo;     // helper sums partners wlo .. k-nle-1
-#pragma unroll
-            for (int u = 0; u < NWS; ++u) {
-                const int sl = lane + 32 * u;
-                if (wlo + sl < k) {
-                    const double2 y = s.ywin[sl];
-                    sm.wbuf[sl] = make_double2(P.p0 * y.x + P.q * y.y, P.q * y.x + P.p1 * y.y);
-                }
-            }
-            // ---- AR(1) term of the successor (old mean) + static partner part
             double hval = 0.0;
-            if (c < 2) hval = s.hab[c];
-            else if (act) {
-                for (int pp = 0; pp < nparts; ++pp) hval += s.H[pp][c - 2];
-            }
-            if (has_next) {
-                double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+            int wlo = 0, nle = 0, cnt = 0;
+            if (DO_INP) {
+                const typename S::Stage& s = sm.st[k & SMASK];
+                double2* wbuf = sm.wbuf[hi];
+                double* hin = sm.hin[hi];
+                double* mprev = sm.mprev[hi];
+                // ---- the window's weights  w0 = p0 y0 + q y1, w1 = q y0 + p1 y1  (structured_mf.py:324)
+                wlo = window_lo(k); nle = min(NL, k - i0); cnt = (k - nle) - wlo;     // the helper sums partners wlo .. k-nle-1
 #pragma unroll
-                for (int q = 0; q + 2 < D; q += 3) {
-                    n0 = fma(pq[q], s.mnext[q], n0);
-                    n1 = fma(pq[q + 1], s.mnext[q + 1], n1);
-                    n2 = fma(pq[q + 2], s.mnext[q + 2], n2);
-                }
-#pragma unroll
-                for (int q = (D / 3) * 3; q < D; ++q) n0 = fma(pq[q], s.mnext[q], n0);
-                hval += (n0 + n1) + n2;                                  // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
-            }
-            // ---- (k, t-1), cheapest source first: the ring of the neighbouring chain warp (same CTA) if it is already
-            // there; the staged look at the global hand-over slot (valid when the predecessor is TAME_LA+ nodes ahead, which
-            // also covers a ring slot that has been overwritten since); wait for the ring; poll the global slot
-            if (has_prev) {
-                double2 hv = make_double2(0.0, 0.0);
-                bool got = false;
-                const long long c0 = clock64();
-                if (use_ring && *((volatile const int*)&pv->c_done) >= k) {
-                    hv = pv->mring[k & (TAME_MR - 1)][cc];
-                    got = __all_sync(0xffffffffu, !act || rtag_ok(hv, k));
-                }
-                if (!got) {
-                    hv = s.hand[cc];
-                    got = __all_sync(0xffffffffu, !act || tag_ok(hv));
-                }
-                if (!got && use_ring) {
-                    if (!tame_wait_smem(&pv->c_done, k, lane, P.abort_flag)) { alive = false; break; }
-                    hv = pv->mring[k & (TAME_MR - 1)][cc];
-                    got = __all_sync(0xffffffffu, !act || rtag_ok(hv, k));
-                }
-                if (!got) {
-                    TameSpin sp;
-                    for (;;) {
-                        if (act) hv = tame_ld_volatile2(hand_prev + (size_t)k * T * D);
-                        if (__all_sync(0xffffffffu, !act || tag_ok(hv))) break;
-                        int ex = 0;
-                        if (lane == 0) ex = sp.expired(P.abort_flag) ? 1 : 0;
-                        if (__shfl_sync(0xffffffffu, ex, 0)) { alive = false; break; }
+                for (int u = 0; u < NWS; ++u) {
+                    const int sl = lane + 32 * u;
+                    if (wlo + sl < k) {
+                        const double2 y = s.ywin[sl];
+                        wbuf[sl] = make_double2(P.p0 * y.x + P.q * y.y, P.q * y.x + P.p1 * y.y);
                     }
-                    if (!alive) break;
                 }
-                wait_hand += clock64() - c0;
-                if (act) sm.mprev[c] = hv.x;
-            }
-            __syncwarp();        // wbuf, mprev
-            // ---- partial window sum over the ring
-            if (R % 4 == 0) {
-                // lane = (partner phase, component quad): NGR quads x PH phases = 32 lanes; a quad lies in one half of z
-                constexpr int NGR = (NV / 4 > 0) ? NV / 4 : 1, PH = 32 / NGR;
-                const int gq = lane % NGR, ph = lane / NGR, x0 = 4 * gq;
-                const double* wsel = reinterpret_cast<const double*>(sm.wbuf) + ((x0 < R) ? 0 : 1);
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-                int jj = ph;
-                for (; jj + PH < cnt; jj += 2 * PH) {
-                    const double wa = wsel[2 * jj], wb = wsel[2 * (jj + PH)];
-                    const double2* za = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
-                    const double2* zb = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj + PH) & RMASK][x0]);
-                    const double2 za0 = za[0], za1 = za[1], zb0 = zb[0], zb1 = zb[1];
-                    a0 = fma(wa, za0.x, a0); a1 = fma(wa, za0.y, a1); a2 = fma(wa, za1.x, a2); a3 = fma(wa, za1.y, a3);
-                    b0 = fma(wb, zb0.x, b0); b1 = fma(wb, zb0.y, b1); b2 = fma(wb, zb1.x, b2); b3 = fma(wb, zb1.y, b3);
+                // ---- AR(1) term of the successor (old mean) + static partner part
+                if (c < 2) hval = s.hab[c];
+                else if (act) {
+                    for (int pp = 0; pp < nparts; ++pp) hval += s.H[pp][c - 2];
                 }
-                if (jj < cnt) {
-                    const double wa = wsel[2 * jj];
-                    const double2* za = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
-                    const double2 za0 = za[0], za1 = za[1];
-                    a0 = fma(wa, za0.x, a0); a1 = fma(wa, za0.y, a1); a2 = fma(wa, za1.x, a2); a3 = fma(wa, za1.y, a3);
-                }
-                a0 += b0; a1 += b1; a2 += b2; a3 += b3;
+                if (has_next) {
+                    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
 #pragma unroll
-                for (int o = NGR; o < 32; o <<= 1) {
-                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-                    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-                }
-                if (lane < NGR) { sm.hin[x0] = a0; sm.hin[x0 + 1] = a1; sm.hin[x0 + 2] = a2; sm.hin[x0 + 3] = a3; }
-            } else {
-                // lane = (partner phase, component pair); NPP pairs x PH phases = 32 lanes
-                constexpr int NPP = (R <= 1) ? 1 : (R <= 2) ? 2 : (R <= 4) ? 4 : 8, PH = 32 / NPP;
-                const int xp = min(lane % NPP, R - 1), ph = lane / NPP, x0 = 2 * xp;
-                const bool a0 = x0 < R, a1 = x0 + 1 < R;
-                double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
-                int jj = ph;
-                for (; jj + PH < cnt; jj += 2 * PH) {
-                    const double2 wa = sm.wbuf[jj], wb = sm.wbuf[jj + PH];
-                    const double2 za = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
-                    const double2 zb = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj + PH) & RMASK][x0]);
-                    s0 = fma(a0 ? wa.x : wa.y, za.x, s0);
-                    u0 = fma(a1 ? wa.x : wa.y, za.y, u0);
-                    s1 = fma(a0 ? wb.x : wb.y, zb.x, s1);
-                    u1 = fma(a1 ? wb.x : wb.y, zb.y, u1);
-                }
-                if (jj < cnt) {
-                    const double2 wa = sm.wbuf[jj];
-                    const double2 za = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
-                    s0 = fma(a0 ? wa.x : wa.y, za.x, s0);
-                    u0 = fma(a1 ? wa.x : wa.y, za.y, u0);
-                }
-                s0 += s1;
-                u0 += u1;
+                    for (int q = 0; q + 2 < D; q += 3) {
+                        n0 = fma(pq[q], s.mnext[q], n0);
+                        n1 = fma(pq[q + 1], s.mnext[q + 1], n1);
+                        n2 = fma(pq[q + 2], s.mnext[q + 2], n2);
+                    }
 #pragma unroll
-                for (int o = NPP; o < 32; o <<= 1) {
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                    u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+                    for (int q = (D / 3) * 3; q < D; ++q) n0 = fma(pq[q], s.mnext[q], n0);
+                    hval += (n0 + n1) + n2;                                  // Phi' Qinv mu_{t+1}     (structured_mf.py:264)
                 }
-                if (lane < NPP && lane < R) { sm.hin[x0] = s0; sm.hin[x0 + 1] = u0; }
-            }
-            if (has_prev) {
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
-#pragma unroll
-                for (int q = 0; q + 2 < D; q += 3) {
-                    p0 = fma(qp[q], sm.mprev[q], p0);
-                    p1 = fma(qp[q + 1], sm.mprev[q + 1], p1);
-                    p2 = fma(qp[q + 2], sm.mprev[q + 2], p2);
+                // ---- (k, t-1), cheapest source first: the ring of the neighbouring chain warp (same CTA) if it is already
+                // there; the staged look at the global hand-over slot (valid when the predecessor is LA+ nodes ahead, which
+                // also covers a ring slot that has been overwritten since); wait for the ring; poll the global slot
+                if (has_prev) {
+                    double2 hv = make_double2(0.0, 0.0);
+                    bool got = false;
+                    const long long c0 = clock64();
+                    if (use_ring && *((volatile const int*)&pv->c_done) >= k) {
+                        hv = pv->mring[k & (TAME_MR - 1)][cc];
+                        got = __all_sync(0xffffffffu, !act || rtag_ok(hv, k));
+                    }
+                    if (!got) {
+                        hv = s.hand[cc];
+                        got = __all_sync(0xffffffffu, !act || tag_ok(hv));
+                    }
+                    if (!got && use_ring) {
+                        if (!tame_wait_smem(&pv->c_done, k, lane, P.abort_flag)) { alive = false; break; }
+                        hv = pv->mring[k & (TAME_MR - 1)][cc];
+                        got = __all_sync(0xffffffffu, !act || rtag_ok(hv, k));
+                    }
+                    if (!got) {
+                        TameSpin sp;
+                        for (;;) {
+                            if (act) hv = tame_ld_volatile2(hand_prev + (size_t)k * T * D);
+                            if (__all_sync(0xffffffffu, !act || tag_ok(hv))) break;
+                            int ex = 0;
+                            if (lane == 0) ex = sp.expired(P.abort_flag) ? 1 : 0;
+                            if (__shfl_sync(0xffffffffu, ex, 0)) { alive = false; break; }
+                        }
+                        if (!alive) break;
+                    }
+                    wait_hand += clock64() - c0;
+                    if (act) mprev[c] = hv.x;
                 }
+                __syncwarp();        // wbuf, mprev
+                // ---- partial window sum over the ring
+                if (R % 4 == 0) {
+                    // lane = (partner phase, component quad): NGR quads x PH phases = 32 lanes; a quad lies in one half of z
+                    constexpr int NGR = (NV / 4 > 0) ? NV / 4 : 1, PH = 32 / NGR;
+                    const int gq = lane % NGR, ph = lane / NGR, x0 = 4 * gq;
+                    const double* wsel = reinterpret_cast<const double*>(wbuf) + ((x0 < R) ? 0 : 1);
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+                    int jj = ph;
+                    for (; jj + PH < cnt; jj += 2 * PH) {
+                        const double wa = wsel[2 * jj], wb = wsel[2 * (jj + PH)];
+                        const double2* za = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                        const double2* zb = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj + PH) & RMASK][x0]);
+                        const double2 za0 = za[0], za1 = za[1], zb0 = zb[0], zb1 = zb[1];
+                        a0 = fma(wa, za0.x, a0); a1 = fma(wa, za0.y, a1); a2 = fma(wa, za1.x, a2); a3 = fma(wa, za1.y, a3);
+                        b0 = fma(wb, zb0.x, b0); b1 = fma(wb, zb0.y, b1); b2 = fma(wb, zb1.x, b2); b3 = fma(wb, zb1.y, b3);
+                    }
+                    if (jj < cnt) {
+                        const double wa = wsel[2 * jj];
+                        const double2* za = reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                        const double2 za0 = za[0], za1 = za[1];
+                        a0 = fma(wa, za0.x, a0); a1 = fma(wa, za0.y, a1); a2 = fma(wa, za1.x, a2); a3 = fma(wa, za1.y, a3);
+                    }
+                    a0 += b0; a1 += b1; a2 += b2; a3 += b3;
 #pragma unroll
-                for (int q = (D / 3) * 3; q < D; ++q) p0 = fma(qp[q], sm.mprev[q], p0);
-                hval += (p0 + p1) + p2;                                  // Qinv Phi mu_{t-1}      (structured_mf.py:258)
-            }
-            __syncwarp();        // hin
-            if (c >= 2 && act) hval += sm.hin[c - 2];
-            // ---- publish node k's inputs
-            typename S::Inp& in = sm.inp[k & IMASK];
-            if (act) {
-                in.hrest[c] = hval;
-                in.mold[c] = s.mold[c];
-                in.pdiag[c] = cdiag + ((c < 2) ? ((c == 0) ? P.p0 : P.p1) * m1 : ((c - 2 < R) ? P.p0 : P.p1) * gd);
-            }
-            if (lane < 2 * nle) {               // wl[q] <-> partner k-1-q
-                const int q = lane >> 1;
-                const double2 w = sm.wbuf[cnt + nle - 1 - q];
-                in.wl[q][lane & 1] = (lane & 1) ? w.y : w.x;
-            }
-            if (k == i0 || (k % TAME_REFRESH) == 0) {
-                // precision column c without the trailing partners (the chain adds them and inverts)
+                    for (int o = NGR; o < 32; o <<= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+                    }
+                    if (lane < NGR) { hin[x0] = a0; hin[x0 + 1] = a1; hin[x0 + 2] = a2; hin[x0 + 3] = a3; }
+                } else {
+                    // lane = (partner phase, component pair); NPP pairs x PH phases = 32 lanes
+                    constexpr int NPP = (R <= 1) ? 1 : (R <= 2) ? 2 : (R <= 4) ? 4 : 8, PH = 32 / NPP;
+                    const int xp = min(lane % NPP, R - 1), ph = lane / NPP, x0 = 2 * xp;
+                    const bool a0 = x0 < R, a1 = x0 + 1 < R;
+                    double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
+                    int jj = ph;
+                    for (; jj + PH < cnt; jj += 2 * PH) {
+                        const double2 wa = wbuf[jj], wb = wbuf[jj + PH];
+                        const double2 za = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                        const double2 zb = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj + PH) & RMASK][x0]);
+                        s0 = fma(a0 ? wa.x : wa.y, za.x, s0);
+                        u0 = fma(a1 ? wa.x : wa.y, za.y, u0);
+                        s1 = fma(a0 ? wb.x : wb.y, zb.x, s1);
+                        u1 = fma(a1 ? wb.x : wb.y, zb.y, u1);
+                    }
+                    if (jj < cnt) {
+                        const double2 wa = wbuf[jj];
+                        const double2 za = *reinterpret_cast<const double2*>(&sm.ring[(wlo + jj) & RMASK][x0]);
+                        s0 = fma(a0 ? wa.x : wa.y, za.x, s0);
+                        u0 = fma(a1 ? wa.x : wa.y, za.y, u0);
+                    }
+                    s0 += s1;
+                    u0 += u1;
+#pragma unroll
+                    for (int o = NPP; o < 32; o <<= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                        u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+                    }
+                    if (lane < NPP && lane < R) { hin[x0] = s0; hin[x0 + 1] = u0; }
+                }
+                if (has_prev) {
+                    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+#pragma unroll
+                    for (int q = 0; q + 2 < D; q += 3) {
+                        p0 = fma(qp[q], mprev[q], p0);
+                        p1 = fma(qp[q + 1], mprev[q + 1], p1);
+                        p2 = fma(qp[q + 2], mprev[q + 2], p2);
+                    }
+#pragma unroll
+                    for (int q = (D / 3) * 3; q < D; ++q) p0 = fma(qp[q], mprev[q], p0);
+                    hval += (p0 + p1) + p2;                                  // Qinv Phi mu_{t-1}      (structured_mf.py:258)
+                }
+                __syncwarp();        // hin
+                if (c >= 2 && act) hval += hin[c - 2];
+                // ---- node k's inputs
+                typename S::Inp& in = sm.inp[k & IMASK];
                 if (act) {
+                    in.hrest[c] = hval;
+                    in.mold[c] = s.mold[c];
+                }
+                if (lane < 2 * nle) {               // wl[q] <-> partner k-1-q
+                    const int q = lane >> 1;
+                    const double2 w = wbuf[cnt + nle - 1 - q];
+                    in.wl[q][lane & 1] = (lane & 1) ? w.y : w.x;
+                }
+            }
+            if (DO_TOT) {
+                // ---- totals side: diag(P) for the naive rule, the precision column at refresh nodes (both without the
+                // trailing partners: the chain adds those)
+                if (P.mode == 0 && act)
+                    sm.pdt[k & IMASK][c] = cdiag + ((c < 2) ? ((c == 0) ? P.p0 : P.p1) * m1 : ((c - 2 < R) ? P.p0 : P.p1) * gd);
+                if ((k == i0 || (k % TAME_REFRESH) == 0) && act) {
                     const size_t cb = (size_t)(has_prev ? 1 : 0) * D * D;
                     double c0v, c1v;
                     if (c < 2) { c0v = ((c == 0) ? P.p0 : P.q) * m1; c1v = ((c == 0) ? P.q : P.p1) * m1; }
                     else { c0v = sA * gy; c1v = sB * gy; }
 #pragma unroll
                     for (int q = 0; q < D; ++q) {
-                        double v = (q == 0) ? c0v : (q == 1) ? c1v : ((q - 2 < R) ? sA : sB) * Gc[(q >= 2) ? q - 2 : 0];
+                        double v = (q == 0) ? c0v : (q == 1) ? c1v : ((q - 2 < R) ? sA : sB) * Gc[(DO_TOT && q >= 2) ? q - 2 : 0];
                         v += P.cst[cb + q * D + c];
                         if (has_next) v += P.cst[2 * D * D + q * D + c];
                         sm.pcol[q * DP + c] = v;
@@ -906,30 +967,43 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
             }
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) *((volatile int*)&sm.h_ready) = k;
+            if (lane == 0) {
+                if (DO_TOT) *((volatile int*)&sm.t_ready) = k;
+                if (DO_INP) *((volatile int*)&sm.ready[k & IMASK]) = k;
+            }
         }
         // ---- next inputs
         __syncwarp();
-        if (k + 1 + LA < i1) stage(k + 1 + LA, is_mine(own_s), own_s.lrow(P.panel));
-        own_s.next(P.panel, P.world);
-        own_k.next(P.panel, P.world);
+        {
+            const int ks = k + STEP * (1 + LA);
+            if (ks < i1) stage(ks, is_mine(own_s), own_s.lrow(P.panel));
+        }
+        own_step(own_s);
+        own_step(own_k);
         tame_cp_async_commit();
     }
     // ---- drain: the last nodes' totals
     tame_cp_async_wait<0>();
     __syncwarp();
+    if (ROLE == TAME_ROLE_INPUT && hi == 0 && FUSED && lane == 0 && (t == 0 || t == P.probe_t)) {      // probes of the first input warp
+        unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
+        dbg[3] = (unsigned long long)wait_unit;
+        dbg[4] = (unsigned long long)wait_hand;
+        dbg[5] = (unsigned long long)wait_chain;
+    }
+    if (!DO_TOT) return;
     for (int jf = max(i0, i1 - 1 - NL); jf < i1 && alive; ++jf) {
+        while (f_at < jf) { own_f.next(P.panel, P.world); ++f_at; }
         if (is_mine(own_f) && !tame_wait_smem(&sm.c_done, jf, lane, P.abort_flag)) { alive = false; break; }
         tot_update(sm.ring[jf & RMASK], FalseT{}, 1.0);
-        own_f.next(P.panel, P.world);
     }
     if (!alive) return;            // watchdog: leave the running totals alone, the caller reports TAME_EHANG
     if (c >= 2 && act) {
         P.tot[(size_t)t * TOT + (c - 2)] = gy;
 #pragma unroll
-        for (int x = 0; x < NV; ++x) P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)] = Gc[x];
+        for (int x = 0; x < (DO_TOT ? NV : 1); ++x) P.tot[(size_t)t * TOT + NV + x * NV + (c - 2)] = Gc[x];
     }
-    if (FUSED && lane == 0 && (t == 0 || t == P.probe_t)) {
+    if (ROLE == TAME_ROLE_ALL && FUSED && lane == 0 && (t == 0 || t == P.probe_t)) {
         unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
         dbg[3] = (unsigned long long)wait_unit;
         dbg[4] = (unsigned long long)wait_hand;
@@ -940,9 +1014,9 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
 // ------------------------------------------------------------------------------------------------------
 // chain warp of time step t
 // ------------------------------------------------------------------------------------------------------
-template <int R, bool FUSED>
-__device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSmem<R>& sm, int lane, int t, int i0, int i1) {
-    using S = TameChainSmem<R>;
+template <int R, bool FUSED, int NH>
+__device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSmem<R, NH>& sm, int lane, int t, int i0, int i1) {
+    using S = TameChainSmem<R, NH>;
     constexpr int D = S::D, NV = S::NV, DP = S::DP;
     constexpr int NL = TAME_NL, IMASK = TAME_NINP - 1, RMASK = TAME_RING - 1;
     const int T = P.T, c = lane, cc = min(c, D - 1);
@@ -972,29 +1046,36 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     for (int k = 0; k < D; ++k) cw[k] = 0.0;
     const bool probe = FUSED && lane == 0 && (t == 0 || t == P.probe_t);     // timing probes (dbg[0..7]: t=0, [8..15]: t=probe_t)
     unsigned long long* dbg = P.dbg + (t == 0 ? 0 : 8);
-    long long wait_in = 0;
+    long long wait_in = 0, wait_next = 0;
     int ncell = 0;
     if (probe) dbg[0] = tame_globaltimer();
     // running addresses of (i, t, c)
     const size_t nstride = (size_t)T * D;
     size_t xoff = ((size_t)i0 * T + t) * D + cc;
 
+    bool prev_mine = true;
     for (int i = i0; i < i1; ++i, xoff += nstride, own_i.next(P.panel, P.world), own_n.next(P.panel, P.world)) {
-        if (!is_mine(own_i)) continue;
+        if (!is_mine(own_i)) { prev_mine = false; continue; }
         const bool refresh = refresh_at(i);
         const bool do_down = (i + 1 < i1) && is_mine(own_n) && !refresh_at(i + 1);
         {
             const long long c0 = clock64();
-            if (!tame_wait_smem(&sm.h_ready, do_down ? i + 1 : i, lane, P.abort_flag)) return;
+            if (!tame_wait_smem(&sm.ready[i & IMASK], i, lane, P.abort_flag)) return;
+            const long long c1 = clock64();
+            if (do_down && !tame_wait_smem(&sm.ready[(i + 1) & IMASK], i + 1, lane, P.abort_flag)) return;
+            wait_next += clock64() - c1;
+            if ((refresh || mode == 0) && !tame_wait_smem(&sm.t_ready, i, lane, P.abort_flag)) return;
+            // the trailing partners' ring rows: written by this warp, or -- foreign nodes with a separate totals warp -- awaited
+            if (NH > 1 && !prev_mine && i > i0 && !tame_wait_smem(&sm.f_done, i - 1, lane, P.abort_flag)) return;
             wait_in += clock64() - c0;
-            if (probe && i == i0) dbg[1] = tame_globaltimer();
         }
+        prev_mine = true;
         const typename S::Inp& in = sm.inp[i & IMASK];
         const int nle = min(NL, i - i0);
         const double mo = in.mold[cc];
         // ---- h: the helper's part + the trailing partners i-1-q (new z in the ring)
         double hval = in.hrest[cc];
-        double pdiag = in.pdiag[cc];
+        double pdiag = (mode == 0) ? sm.pdt[i & IMASK][cc] : 0.0;
 #pragma unroll
         for (int q = 0; q < NL; ++q) {
             const double zj = sm.ring[(i - 1 - q) & RMASK][zc];
@@ -1131,27 +1212,50 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     }
     if (probe) {
         dbg[2] = tame_globaltimer();
+        dbg[1] = (unsigned long long)wait_next;
         dbg[6] = (unsigned long long)ncell;
         dbg[7] = (unsigned long long)wait_in;
     }
 }
 
-// One chain CTA: warps 0..WPC-1 are the chain warps of WPC consecutive time steps (one per SM sub-partition), warps
-// WPC..2*WPC-1 their helpers.
-template <int R, bool FUSED>
+// One chain CTA (8 warps).  NH = 1: warps 0..3 are the chain warps of 4 consecutive time steps (one per SM sub-partition),
+// warps 4..7 their helpers.  NH = 2: two time steps, each with a chain warp, a totals warp and two input warps; the roles of
+// the second time step are rotated by one so that every sub-partition carries one chain-or-totals warp and one input warp.
+template <int NH>
+struct TameTeam {
+    static constexpr int TPC = (NH == 1) ? 4 : 2;        // time steps per chain CTA
+};
+template <int R, bool FUSED, int NH>
 __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned char* smem_raw, int cta, int i0, int i1) {
-    using S = TameChainSmem<R>;
-    S* warps = reinterpret_cast<S*>(smem_raw);
+    using S = TameChainSmem<R, NH>;
+    constexpr int TPC = TameTeam<NH>::TPC;
+    S* team = reinterpret_cast<S*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < TAME_CHAIN_WPC) { warps[threadIdx.x].h_ready = i0 - 1; warps[threadIdx.x].c_done = i0 - 1; }
+    if (threadIdx.x < TPC) {
+        S& q = team[threadIdx.x];
+        for (int k = 0; k < TAME_NINP; ++k) q.ready[k] = i0 - 1;
+        q.t_ready = i0 - 1; q.f_done = i0 - 1; q.c_done = i0 - 1;
+    }
     __syncthreads();
-    const bool is_helper = warp >= TAME_CHAIN_WPC;
-    const int wpair = warp - (is_helper ? TAME_CHAIN_WPC : 0);
-    if (wpair >= TAME_CHAIN_WPC) return;
-    const int t = cta * TAME_CHAIN_WPC + wpair;
-    if (t >= P.T) return;
-    if (is_helper) tame_chain_helper<R, FUSED>(P, warps[wpair], (wpair > 0) ? &warps[wpair - 1] : nullptr, lane, t, i0, i1);
-    else tame_chain_warp<R, FUSED>(P, warps[wpair], lane, t, i0, i1);
+    if (NH == 1) {
+        const bool is_helper = warp >= TPC;
+        const int tg = warp - (is_helper ? TPC : 0);
+        if (tg >= TPC) return;
+        const int t = cta * TPC + tg;
+        if (t >= P.T) return;
+        if (is_helper) tame_chain_helper<R, FUSED, NH, TAME_ROLE_ALL>(P, team[tg], (tg > 0) ? &team[tg - 1] : nullptr, lane, t, 0, i0, i1);
+        else tame_chain_warp<R, FUSED, NH>(P, team[tg], lane, t, i0, i1);
+    } else {
+        const int tg = warp >> 2;
+        if (tg >= TPC) return;
+        const int role = ((warp & 3) + 4 - tg) & 3;           // 0 chain, 1 totals, 2/3 input warps
+        const int t = cta * TPC + tg;
+        if (t >= P.T) return;
+        const S* pv = (tg > 0) ? &team[tg - 1] : nullptr;
+        if (role == 0) tame_chain_warp<R, FUSED, NH>(P, team[tg], lane, t, i0, i1);
+        else if (role == 1) tame_chain_helper<R, FUSED, NH, TAME_ROLE_TOTALS>(P, team[tg], pv, lane, t, 0, i0, i1);
+        else tame_chain_helper<R, FUSED, NH, TAME_ROLE_INPUT>(P, team[tg], pv, lane, t, role - 2, i0, i1);
+    }
 }
 
 
@@ -1188,7 +1292,7 @@ __global__ void __launch_bounds__(256) k_covblend(TameParams P) {
 template <int R>
 __global__ void __launch_bounds__(2 * TAME_CHAIN_WPC * 32, 1) k_chain(TameParams P, int i0, int i1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tame_chain_body<R, false>(P, smem_raw, blockIdx.x, i0, i1);
+    tame_chain_body<R, false, 1>(P, smem_raw, blockIdx.x, i0, i1);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1203,12 +1307,12 @@ __global__ void __launch_bounds__(2 * TAME_CHAIN_WPC * 32, 1) k_chain(TameParams
 // Every Y entry is read exactly once per sweep; the schedule is the reference's.
 // grid = n_chain_ctas + workers (all co-resident), block 256, dynamic smem = max of the two roles.
 // ------------------------------------------------------------------------------------------------------
-template <int R, int RW>
+template <int R, int RW, int NH>
 __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(8 * RW == TAME_SB, "a streaming unit is one sub-block of rows");
     if ((int)blockIdx.x < P.n_chain_ctas) {
-        tame_chain_body<R, true>(P, smem_raw, blockIdx.x, 0, P.n);
+        tame_chain_body<R, true, NH>(P, smem_raw, blockIdx.x, 0, P.n);
         return;
     }
     constexpr int NV = 2 * R, JC = TameStream<R, RW>::JC;
@@ -1829,7 +1933,7 @@ struct TameOps {
     cudaError_t (*chain)(const TameParams&, int i0, int i1, cudaStream_t);
     void (*covblend)(const TameParams&, cudaStream_t);
     cudaError_t (*sweep_fused)(const TameParams&, cudaStream_t);
-    int (*sweep_capacity)();
+    int (*sweep_capacity)(int nh);
     int (*chain_max_T)();
     void (*llmse)(const TameParams&, double* partial, int* nblocks, int symmetric, cudaStream_t);
     void (*cellterms)(const TameParams&, double logdetS0, double logdetQ, double* partial, int nblocks, cudaStream_t);

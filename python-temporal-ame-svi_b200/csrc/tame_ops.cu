@@ -62,7 +62,7 @@ void launch_contract(const TameParams& P, int k0, int k1, int j0, int j1, int tr
     tame_count_launch(1);
 }
 
-size_t chain_smem_bytes() { return TAME_CHAIN_WPC * sizeof(TameChainSmem<R>); }
+size_t chain_smem_bytes() { return TAME_CHAIN_WPC * sizeof(TameChainSmem<R, 1>); }
 
 cudaError_t launch_chain(const TameParams& P, int i0, int i1, cudaStream_t st) {
     static PerDevice configured;
@@ -85,27 +85,34 @@ void launch_covblend(const TameParams& P, cudaStream_t st) {
     tame_count_launch(1);
 }
 
-size_t sweep_smem_bytes() { return chain_smem_bytes() > TameStream<R, RW>::SMEM ? chain_smem_bytes() : TameStream<R, RW>::SMEM; }
-
-// co-resident CTAs of k_sweep on the current device
-int sweep_capacity() {
+// the fused sweep in its two team shapes (NH = 1: 4 time steps per chain CTA; NH = 2: 2 time steps, separate totals / input warps)
+template <int NH>
+size_t sweep_smem_bytes() {
+    const size_t chain = TameTeam<NH>::TPC * sizeof(TameChainSmem<R, NH>);
+    return chain > TameStream<R, RW>::SMEM ? chain : TameStream<R, RW>::SMEM;
+}
+template <int NH>
+int sweep_capacity_nh() {
     static PerDevice cap;
     const int dev = current_device();
     int c = cap.v[dev].load();
     if (c < 0) {
         int per = 0;
-        cudaFuncSetAttribute(k_sweep<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes());
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep<R, RW>, 256, sweep_smem_bytes());
+        cudaFuncSetAttribute(k_sweep<R, RW, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<NH>());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep<R, RW, NH>, 256, sweep_smem_bytes<NH>());
         c = device_sms(dev) * per;
         cap.v[dev].store(c);
     }
     return c;
 }
+// co-resident CTAs of k_sweep on the current device
+int sweep_capacity(int nh) { return nh == 2 ? sweep_capacity_nh<2>() : sweep_capacity_nh<1>(); }
 
-cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
-    const int capacity = sweep_capacity();
+template <int NH>
+cudaError_t launch_sweep_nh(const TameParams& P, cudaStream_t st) {
+    const int capacity = sweep_capacity_nh<NH>();
     TameParams p = P;
-    p.n_chain_ctas = (P.T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC;
+    p.n_chain_ctas = (P.T + TameTeam<NH>::TPC - 1) / TameTeam<NH>::TPC;
     const int nunits = ((P.n + TAME_SB - 1) / TAME_SB) * ((P.T + 31) / 32) * P.nparts;
     int workers = capacity - p.n_chain_ctas < nunits ? capacity - p.n_chain_ctas : nunits;
     if (workers < 1) return cudaErrorLaunchOutOfResources;
@@ -116,7 +123,21 @@ cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
     if ((long)workers > want) workers = (int)want;
     void* args[] = {(void*)&p};
     tame_count_launch(1);
-    return cudaLaunchCooperativeKernel((void*)k_sweep<R, RW>, dim3(p.n_chain_ctas + workers), dim3(256), args, sweep_smem_bytes(), st);
+    return cudaLaunchCooperativeKernel((void*)k_sweep<R, RW, NH>, dim3(p.n_chain_ctas + workers), dim3(256), args, sweep_smem_bytes<NH>(), st);
+}
+
+// Team shape: the wide team (NH = 2) needs twice the chain CTAs; it pays when the chain, not the streaming, bounds the
+// sweep -- several GPUs (the streaming shrinks with the rank count, the chain does not) or a small problem -- and
+// when enough SMs are left for the streaming CTAs.  TAME_NH=1|2 overrides.
+int pick_nh(const TameParams& P) {
+    int nh = (P.world >= 2 || (long)P.n * P.n * P.T <= (long)4096 * 4096 * 64) ? 2 : 1;
+    if (const char* v = getenv("TAME_NH")) nh = (atoi(v) == 2) ? 2 : 1;
+    if (nh == 2 && (P.T + 1) / 2 + 8 > sweep_capacity_nh<2>()) nh = 1;
+    return nh;
+}
+
+cudaError_t launch_sweep_fused(const TameParams& P, cudaStream_t st) {
+    return pick_nh(P) == 2 ? launch_sweep_nh<2>(P, st) : launch_sweep_nh<1>(P, st);
 }
 
 int chain_max_T() {

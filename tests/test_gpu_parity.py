@@ -101,14 +101,17 @@ def _random_problem(n, T, r, seed, rho=0.5, ar=0.8):
 SHAPES = [(70, 3, 1), (65, 7, 2), (130, 5, 3), (96, 33, 4), (64, 4, 5), (100, 2, 6), (67, 9, 7), (129, 6, 8), (200, 40, 2)]
 
 
-@pytest.fixture(params=["fused", "panel"])
+@pytest.fixture(params=["fused", "fused-nh1", "panel"])
 def sweep_path(request, monkeypatch):
-    """Both schedulers of the same sweep: the persistent fused kernel (single-GPU default) and the stream-ordered
-    per-panel launches (the multi-GPU path, forced here on one GPU)."""
+    """The schedulers of the same sweep: the persistent fused kernel in both team shapes (chain + totals + two input warps
+    per time step -- the default at these sizes -- and chain + one helper, TAME_NH=1) and the stream-ordered per-panel
+    launches (the multi-GPU fallback, forced here on one GPU)."""
+    monkeypatch.delenv("TAME_SWEEP", raising=False)
+    monkeypatch.delenv("TAME_NH", raising=False)
     if request.param == "panel":
         monkeypatch.setenv("TAME_SWEEP", "panel")
-    else:
-        monkeypatch.delenv("TAME_SWEEP", raising=False)
+    elif request.param == "fused-nh1":
+        monkeypatch.setenv("TAME_NH", "1")
     return request.param
 
 
