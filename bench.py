@@ -730,6 +730,13 @@ def extra_config5(lib, _lib, dev, max_iter=150, tolerance=1e-4):
             f += 1
     torch.cuda.synchronize(dev)
     el = np.zeros((nf, max_iter)); ms = np.zeros((nf, max_iter)); nd = (C.c_int32 * nf)()
+    # warm-up (module load of the r=2 kernels, allocator): a few iterations of the first fits, then restore their state
+    warm = min(nf, 16)
+    saved = [(keep[f][2].clone(), keep[f][3].clone()) for f in range(warm)]
+    _lib.check(lib.tame_fit_batch(warm, cfgs, Yp, Mp, Cp, 2, 0.0, _lib.dptr(el), _lib.dptr(ms), nd, 0))
+    for f in range(warm):
+        keep[f][2].copy_(saved[f][0]); keep[f][3].copy_(saved[f][1])
+    torch.cuda.synchronize(dev)
     launches0 = lib.tame_launch_count()
     t0 = time.time()
     _lib.check(lib.tame_fit_batch(nf, cfgs, Yp, Mp, Cp, max_iter, tolerance, _lib.dptr(el), _lib.dptr(ms), nd, 0))

@@ -183,6 +183,9 @@ int tame_comm_init(tame_handle* h, const void* id128_host);
  * broadcast per 64-node block) is used. */
 int tame_ipc_export(tame_handle* h, void* handle64_host);
 int tame_ipc_import(tame_handle* h, const void* handles_host);
+/* Same, for ranks that live in ONE process (one handle per device): every rank's handle is passed directly, peer access
+ * is enabled between the devices and the hand-over buffers are used through their plain device pointers. */
+int tame_peer_attach(tame_handle* h, tame_handle* const* all_handles);
 /* all-gather the X_cov rows (X_mean is already replicated) so every rank holds the full state */
 int tame_gather_state(tame_handle* h);
 

@@ -353,6 +353,39 @@ static void matmul(const double* A, const double* B, double* C, int d, bool tran
         }
 }
 
+static std::vector<double> constant_block(const tame_config* cfg, int d) {
+    std::vector<double> c(6 * d * d);
+    memcpy(&c[0], cfg->S0inv, sizeof(double) * d * d);
+    memcpy(&c[d * d], cfg->Qinv, sizeof(double) * d * d);
+    matmul(cfg->Qinv, cfg->Phi, &c[3 * d * d], d, false);          // Qinv Phi
+    matmul(cfg->Phi, &c[3 * d * d], &c[2 * d * d], d, true);       // Phi' (Qinv Phi)      structured_mf.py:262
+    matmul(cfg->Phi, cfg->Qinv, &c[4 * d * d], d, true);           // Phi' Qinv            structured_mf.py:264
+    memcpy(&c[5 * d * d], cfg->Phi, sizeof(double) * d * d);
+    return c;
+}
+
+// Point an existing single-GPU handle at another fit of the SAME shape (n, T, r, device): new hyper-parameters, mode and
+// learning rate; Y and the state are bound afresh by the caller.  tame_fit_batch pools its handles with this (a handle is
+// ~20 device allocations, and cudaFree synchronises the whole device).
+static int tame_reconfigure(tame_handle* h, const tame_config* cfg) {
+    if (cfg->n != h->cfg.n || cfg->T != h->cfg.T || cfg->r != h->cfg.r || cfg->device != h->cfg.device || cfg->world != 1 || h->P.world != 1)
+        return fail(TAME_EINVAL, "tame_reconfigure: shape mismatch");
+    if (cfg->mode < 0 || cfg->mode > 2) return fail(TAME_EINVAL, "unknown mode %d", cfg->mode);
+    if (!cfg->Phi || !cfg->Qinv || !cfg->S0inv) return fail(TAME_EINVAL, "Phi/Qinv/S0inv must be given");
+    const std::vector<double> c = constant_block(cfg, h->d);
+    h->cfg = *cfg;
+    h->cfg.Phi = h->cfg.Qinv = h->cfg.S0inv = nullptr;
+    CK(cudaMemcpyAsync(h->cst, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));                        // `c` is pageable host memory on this stack
+    TameParams& P = h->P;
+    P.mode = cfg->mode;
+    P.lr = cfg->lr;
+    P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
+    P.Y = nullptr; P.Xm = nullptr; P.Xc = nullptr;
+    h->y_bound = h->state_bound = h->y_symmetric = false;
+    return TAME_OK;
+}
+
 extern "C" {
 
 const char* tame_version(void) { return "tame_b200 0.1.0 (sm_100a, fp64)"; }
@@ -384,13 +417,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     if (T > h->ops->chain_max_T()) { delete h; return fail(TAME_EINVAL, "T=%d exceeds the co-resident capacity of the chain kernel", T); }
 
     // constant matrices: S0inv, Qinv, Phi'QinvPhi, QinvPhi, Phi'Qinv, Phi
-    std::vector<double> c(6 * d * d), tmp(d * d);
-    memcpy(&c[0], cfg->S0inv, sizeof(double) * d * d);
-    memcpy(&c[d * d], cfg->Qinv, sizeof(double) * d * d);
-    matmul(cfg->Qinv, cfg->Phi, &c[3 * d * d], d, false);          // Qinv Phi
-    matmul(cfg->Phi, &c[3 * d * d], &c[2 * d * d], d, true);       // Phi' (Qinv Phi)      structured_mf.py:262
-    matmul(cfg->Phi, cfg->Qinv, &c[4 * d * d], d, true);           // Phi' Qinv            structured_mf.py:264
-    memcpy(&c[5 * d * d], cfg->Phi, sizeof(double) * d * d);
+    std::vector<double> c = constant_block(cfg, d);
     h->cfg.Phi = h->cfg.Qinv = h->cfg.S0inv = nullptr;             // host pointers are not retained
 
     const int TOT = h->ops->tot;
@@ -449,7 +476,10 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.probe_t = T - 1;
     if (const char* v = getenv("TAME_PROBE_T")) P.probe_t = std::max(0, std::min(T - 1, atoi(v)));
     for (int k = 0; k < 7; ++k) P.hand_peer[k] = nullptr;
-    CK(cudaDeviceSynchronize());      // the zeroed hand-over slots must be in place before any peer can write into them
+    // the zeroed hand-over slots / stamps must be in place before the first kernel on the handle's (possibly non-blocking)
+    // stream, and -- multi-GPU -- before any peer can write into them
+    if (world > 1) CK(cudaDeviceSynchronize());
+    else CK(cudaStreamSynchronize(cudaStreamLegacy));
 
     h->nb_ll = h->ops->llmse_blocks(P);
     h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
@@ -710,22 +740,29 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
         cudaStream_t st = nullptr;
         int rc = TAME_OK;
         if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = fail(TAME_ECUDA, "cudaStreamCreate failed in tame_fit_batch");
+        std::vector<tame_handle*> pool;           // this worker's handles, one per shape it has met
         while (rc == TAME_OK && first_rc.load() == TAME_OK) {
             const int f = next.fetch_add(1);
             if (f >= n_fits) break;
+            const tame_config& cf = cfgs[f];
             tame_handle* h = nullptr;
-            rc = tame_create(&cfgs[f], &h);
-            if (rc == TAME_OK) rc = tame_set_stream(h, st);
+            for (tame_handle* q : pool)
+                if (q->cfg.n == cf.n && q->cfg.T == cf.T && q->cfg.r == cf.r && q->cfg.device == cf.device && cf.world == 1) { h = q; break; }
+            if (h) rc = tame_reconfigure(h, &cf);
+            else {
+                rc = tame_create(&cf, &h);
+                if (rc == TAME_OK) { pool.push_back(h); rc = tame_set_stream(h, st); }
+            }
             if (rc == TAME_OK) rc = tame_bind_Y(h, Y_dev[f]);
             if (rc == TAME_OK) rc = tame_bind_state(h, Xm_dev[f], Xc_dev[f]);
             if (rc == TAME_OK)
                 rc = tame_fit(h, max_iter, tolerance, elbo_traces ? elbo_traces + (size_t)f * max_iter : nullptr,
                               mse_traces ? mse_traces + (size_t)f * max_iter : nullptr, &n_done[f]);
-            if (h) {
-                std::string keep = g_err;
-                tame_destroy(h);
-                g_err = keep;
-            }
+        }
+        {
+            std::string keep = g_err;
+            for (tame_handle* q : pool) tame_destroy(q);
+            g_err = keep;
         }
         if (rc != TAME_OK) {
             int expected = TAME_OK;
@@ -808,6 +845,33 @@ int tame_ipc_import(tame_handle* h, const void* handles_host) {
         CK(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
         h->peer_base[k] = base;
         h->P.hand_peer[k] = (double2*)base;
+        ++k;
+    }
+    h->npeers = k;
+    h->P.npeers = h->fused_multi ? k : 0;
+    return TAME_OK;
+}
+
+int tame_peer_attach(tame_handle* h, tame_handle* const* all_handles) {
+    if (!h || !all_handles) return fail(TAME_EINVAL, "null argument");
+    if (h->P.world == 1) return TAME_OK;
+    if (h->P.world > 8) return fail(TAME_EINVAL, "the fused multi-GPU sweep supports up to 8 ranks");
+    CK(cudaSetDevice(h->cfg.device));
+    int k = 0;
+    for (int r = 0; r < h->P.world; ++r) {
+        if (r == h->P.rank) continue;
+        tame_handle* o = all_handles[r];
+        if (!o || o->P.world != h->P.world || o->P.rank != r || o->P.n != h->P.n || o->P.T != h->P.T || o->d != h->d)
+            return fail(TAME_EINVAL, "tame_peer_attach: handle of rank %d does not belong to this fit", r);
+        if (o->cfg.device != h->cfg.device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, h->cfg.device, o->cfg.device));
+            if (!can) return fail(TAME_ECUDA, "device %d cannot access device %d (no NVLink/P2P path)", h->cfg.device, o->cfg.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(TAME_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+        }
+        h->P.hand_peer[k] = o->hand;
         ++k;
     }
     h->npeers = k;

@@ -13,8 +13,8 @@ include/tame_b200.h; there is no CPU fallback.
 """
 from .models import BaseAMEModel, StaticAMEModel, TemporalAMEModel
 from .inference import (BaseVariationalInference, BaseTemporalVariationalInference, TemporalAMENaiveMFVI,
-                        TemporalAMEStructuredMFVI)
+                        TemporalAMEStructuredMFVI, fit_batch)
 
 __version__ = "0.1.0"
 __all__ = ["BaseAMEModel", "StaticAMEModel", "TemporalAMEModel", "BaseVariationalInference",
-           "BaseTemporalVariationalInference", "TemporalAMENaiveMFVI", "TemporalAMEStructuredMFVI"]
+           "BaseTemporalVariationalInference", "TemporalAMENaiveMFVI", "TemporalAMEStructuredMFVI", "fit_batch"]

@@ -64,6 +64,7 @@ SIGNATURES = {
     "tame_comm_init": (C.c_int, [_P, _P]),
     "tame_ipc_export": (C.c_int, [_P, _P]),
     "tame_ipc_import": (C.c_int, [_P, _P]),
+    "tame_peer_attach": (C.c_int, [_P, _P]),
     "tame_gather_state": (C.c_int, [_P]),
     "tame_last_timing": (C.c_int, [_P, _DP, _DP, _DP, _DP, _DP]),
     "tame_set_timing": (C.c_int, [_P, C.c_int32]),

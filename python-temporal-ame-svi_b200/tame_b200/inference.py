@@ -23,6 +23,35 @@ import numpy as np
 import torch
 
 from . import _lib
+from .sharding import DEFAULT_PANEL, owned_rows
+
+
+def _fit_config(vi, device_index: int, world: int = 1, rank: int = 0, panel: int = 0):
+    """tame_config for a VI object: what the reference reads from `model` inside the loop
+    (structured_mf.py:127-128,154-158,177-180,229-237).  Returns (cfg, keepalive arrays)."""
+    model = vi.model
+    d = vi.d
+    f64 = torch.float64
+    R = model.R.detach().to("cpu", f64)
+    Rinv = model.R_inv.detach().to("cpu", f64)
+    S0 = torch.zeros(d, d, dtype=f64)
+    S0[:2, :2] = model.Sigma.detach().to("cpu", f64)
+    S0[2:, 2:] = model.Psi.detach().to("cpu", f64)
+    Q = model.Q.detach().to("cpu", f64)
+    keep = [np.ascontiguousarray(model.Phi.detach().to("cpu", f64).numpy()),
+            np.ascontiguousarray(torch.linalg.inv(Q).numpy()),          # structured_mf.py:231
+            np.ascontiguousarray(torch.linalg.inv(S0).numpy())]         # structured_mf.py:237
+    cfg = _lib.TameConfig()
+    cfg.n, cfg.T, cfg.r, cfg.mode = vi.n, vi.T, vi.r, vi._mode
+    cfg.lr = float(vi.lr)
+    for k, v in enumerate(Rinv.reshape(-1).tolist()):
+        cfg.Rinv[k] = v
+    cfg.logdet_R = float(torch.logdet(R))
+    cfg.logdet_Q = float(torch.logdet(Q))
+    cfg.logdet_S0 = float(torch.logdet(S0))
+    cfg.Phi, cfg.Qinv, cfg.S0inv = (_lib.dptr(a) for a in keep)
+    cfg.device, cfg.world, cfg.rank, cfg.panel = device_index, world, rank, panel
+    return cfg, keep
 
 
 class _Engine:
@@ -39,25 +68,7 @@ class _Engine:
         model = vi.model
         n, T, r, d = vi.n, vi.T, vi.r, vi.d
         f64 = torch.float64
-        R = model.R.detach().to("cpu", f64)
-        Rinv = model.R_inv.detach().to("cpu", f64)
-        S0 = torch.zeros(d, d, dtype=f64)
-        S0[:2, :2] = model.Sigma.detach().to("cpu", f64)
-        S0[2:, 2:] = model.Psi.detach().to("cpu", f64)
-        Q = model.Q.detach().to("cpu", f64)
-        self._Phi = np.ascontiguousarray(model.Phi.detach().to("cpu", f64).numpy())
-        self._Qinv = np.ascontiguousarray(torch.linalg.inv(Q).numpy())          # structured_mf.py:231
-        self._S0inv = np.ascontiguousarray(torch.linalg.inv(S0).numpy())        # structured_mf.py:237
-        cfg = _lib.TameConfig()
-        cfg.n, cfg.T, cfg.r, cfg.mode = n, T, r, vi._mode
-        cfg.lr = float(vi.lr)
-        for k, v in enumerate(Rinv.reshape(-1).tolist()):
-            cfg.Rinv[k] = v
-        cfg.logdet_R = float(torch.logdet(R))
-        cfg.logdet_Q = float(torch.logdet(Q))
-        cfg.logdet_S0 = float(torch.logdet(S0))
-        cfg.Phi, cfg.Qinv, cfg.S0inv = _lib.dptr(self._Phi), _lib.dptr(self._Qinv), _lib.dptr(self._S0inv)
-        cfg.device, cfg.world, cfg.rank, cfg.panel = dev.index, world, rank, panel
+        cfg, self._keep = _fit_config(vi, dev.index, world, rank, panel)
         self.cfg = cfg
         self.handle = C.c_void_p()
         with torch.cuda.device(dev):
@@ -93,6 +104,115 @@ class _Engine:
         if self.handle:
             self.lib.tame_destroy(self.handle)
             self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _MultiEngine:
+    """One fit sharded over several GPUs of this box, driven from ONE process: a libtame handle per device (rows of Y
+    dealt in 64-node panels, X_mean replicated), NCCL for the ELBO all-reduce / the X_cov gather, the fused sweep with
+    NVLink peer hand-over (tame_peer_attach).  The ranks' calls are issued from one host thread each (ctypes drops the
+    GIL), because every rank's kernels wait for the others'."""
+
+    def __init__(self, vi, devices):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tame_b200 needs CUDA devices (sm_100a); there is no CPU fallback")
+        from concurrent.futures import ThreadPoolExecutor
+        self.lib = _lib.load()
+        def as_dev(dv):
+            if isinstance(dv, int):
+                return torch.device("cuda", dv)
+            dd = torch.device(dv)
+            return torch.device("cuda", dd.index if dd.index is not None else 0)
+        self.devs = [as_dev(dv) for dv in devices]
+        self.world = len(self.devs)
+        if self.world < 2 or self.world > 8 or len({dv.index for dv in self.devs}) != self.world:
+            raise ValueError("devices= needs 2..8 distinct CUDA devices")
+        n, T, r, d = vi.n, vi.T, vi.r, vi.d
+        panel = DEFAULT_PANEL
+        if n % panel:
+            raise ValueError(f"the multi-GPU fit deals nodes in panels of {panel}: n_nodes={n} must be a multiple of {panel}")
+        self.device = self.devs[0]
+        self.pool = ThreadPoolExecutor(max_workers=self.world)
+        f64 = torch.float64
+        Yfull = (vi.Y if vi.Y is not None else vi.model.Y).detach()
+        if tuple(Yfull.shape) != (n, n, T, 2):
+            raise ValueError(f"Y has shape {tuple(Yfull.shape)}, expected {(n, n, T, 2)}")
+        self.rows = [owned_rows(n, panel, self.world, rk) for rk in range(self.world)]
+        self.handles, self.Y, self.Xm, self.Xc, self._keep = [], [], [], [], []
+        for rk, dv in enumerate(self.devs):
+            cfg, keep = _fit_config(vi, dv.index, self.world, rk, panel)
+            h = C.c_void_p()
+            with torch.cuda.device(dv):
+                _lib.check(self.lib.tame_create(C.byref(cfg), C.byref(h)))
+                self.Y.append(torch.cat([Yfull[a:b] for a, b in self.rows[rk]], 0).to(dv, f64).contiguous())
+                self.Xm.append(torch.empty(n, T, d, dtype=f64, device=dv))
+                self.Xc.append(torch.empty(n, T, d, d, dtype=f64, device=dv))
+                torch.cuda.synchronize(dv)
+            self.handles.append(h)
+            self._keep.append(keep)
+        uid = (C.c_ubyte * 128)()
+        _lib.check(self.lib.tame_comm_unique_id(uid))
+        self._each(lambda rk: self.lib.tame_comm_init(self.handles[rk], uid))
+        table = (C.c_void_p * self.world)(*[h.value for h in self.handles])
+        for rk in range(self.world):
+            _lib.check(self.lib.tame_peer_attach(self.handles[rk], table))
+        self._each(lambda rk: self.lib.tame_bind_Y(self.handles[rk], self.Y[rk].data_ptr()))
+        for rk in range(self.world):
+            _lib.check(self.lib.tame_bind_state(self.handles[rk], self.Xm[rk].data_ptr(), self.Xc[rk].data_ptr()))
+        self._out6 = [(C.c_double * 6)() for _ in range(self.world)]
+        self._gathered = True
+
+    def _each(self, call):
+        """call(rank) -> C-ABI return code, on every rank concurrently; the first failure raises."""
+        def run(rk):
+            with torch.cuda.device(self.devs[rk]):
+                return call(rk), (self.lib.tame_last_error() or b"").decode()
+        res = list(self.pool.map(run, range(self.world)))
+        for rc, msg in res:
+            if rc != 0:
+                raise RuntimeError(f"libtame_b200: error {rc}: {msg}")
+
+    def upload(self, X_mean: torch.Tensor, X_cov: torch.Tensor):
+        for rk, dv in enumerate(self.devs):
+            self.Xm[rk].copy_(X_mean.detach().to(dv, torch.float64))
+            self.Xc[rk].copy_(X_cov.detach().to(dv, torch.float64))
+            torch.cuda.synchronize(dv)
+
+    @property
+    def X_mean(self):
+        return self.Xm[0]
+
+    @property
+    def X_cov(self):
+        if not self._gathered:        # X_cov rows of foreign nodes are only valid after the gather
+            self._each(lambda rk: self.lib.tame_gather_state(self.handles[rk]))
+            self._gathered = True
+        return self.Xc[0]
+
+    def sweep(self):
+        self._each(lambda rk: self.lib.tame_sweep(self.handles[rk]))
+        self._gathered = False
+
+    def elbo_mse(self):
+        self._each(lambda rk: self.lib.tame_elbo_mse(self.handles[rk], self._out6[rk]))
+        return list(self._out6[0])
+
+    def iterate(self):
+        self._each(lambda rk: self.lib.tame_iterate(self.handles[rk], self._out6[rk]))
+        self._gathered = False
+        return list(self._out6[0])
+
+    def close(self):
+        for h in self.handles:
+            if h:
+                self.lib.tame_destroy(h)
+        self.handles = []
+        self.pool.shutdown(wait=False)
 
     def __del__(self):
         try:
@@ -182,11 +302,12 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
 
     _mode = _lib.MODE_GOOD
 
-    def __init__(self, model, learning_rate: float = 0.01, seed: int = 42, device=None):
+    def __init__(self, model, learning_rate: float = 0.01, seed: int = 42, device=None, devices=None):
         self.T = model.T
         self.d = model.d
         self.r = model.r
         self._device = device
+        self._devices = list(devices) if devices is not None else None      # additive keyword: shard ONE fit over these GPUs
         self._engine: Optional[_Engine] = None
         self._host_mean: Optional[torch.Tensor] = None
         self._host_cov: Optional[torch.Tensor] = None
@@ -229,7 +350,10 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
             if self.r < 1 or self.r > _lib.MAX_R:
                 raise ValueError(f"latent_dim={self.r} is outside the supported range 1..{_lib.MAX_R}")
             self.Y = self.model.Y if self.Y is None else self.Y
-            self._engine = _Engine(self, self._device)
+            if self._devices is not None and len(self._devices) > 1:
+                self._engine = _MultiEngine(self, self._devices)
+            else:
+                self._engine = _Engine(self, self._devices[0] if self._devices else self._device)
             self._host_newer = True
         if self._host_newer:
             self._engine.upload(self._host_mean, self._host_cov)
@@ -308,9 +432,9 @@ class TemporalAMENaiveMFVI(BaseTemporalVariationalInference):
 
     _mode = _lib.MODE_NAIVE
 
-    def __init__(self, model, learning_rate: float = 1.0, init_scale: float = 0.1, seed: int = 42, device=None):
+    def __init__(self, model, learning_rate: float = 1.0, init_scale: float = 0.1, seed: int = 42, device=None, devices=None):
         self.init_scale = init_scale
-        super().__init__(model, learning_rate, seed, device=device)
+        super().__init__(model, learning_rate, seed, device=device, devices=devices)
 
     def _initialize_variational_params(self) -> None:
         """naive_mf.py:71-87: one randn for the means, 0.5*I covariances."""
@@ -336,12 +460,12 @@ class TemporalAMEStructuredMFVI(BaseTemporalVariationalInference):
     (structured_mf.py:28-338)."""
 
     def __init__(self, model, factorization: str = "good", learning_rate: float = 1.0, init_scale: float = 0.1,
-                 cov_init_scale: float = 0.5, seed: int = 42, device=None):
+                 cov_init_scale: float = 0.5, seed: int = 42, device=None, devices=None):
         self.factorization = factorization
         self.init_scale = init_scale
         self.cov_init_scale = cov_init_scale
         self._mode = _lib.MODE_BAD if factorization == "bad" else _lib.MODE_GOOD
-        super().__init__(model, learning_rate, seed, device=device)
+        super().__init__(model, learning_rate, seed, device=device, devices=devices)
 
     def _initialize_variational_params(self) -> None:
         """structured_mf.py:74-113.  The per-block randn calls are kept in the reference's order (means first, then
@@ -374,3 +498,57 @@ class TemporalAMEStructuredMFVI(BaseTemporalVariationalInference):
 
     def get_factorization_type(self) -> str:
         return self.factorization
+
+
+def fit_batch(vis, max_iter: int = 100, tolerance: float = 1e-4, device=None, n_streams: int = 0):
+    """Fit many independent VI objects in ONE call (tame_fit_batch; BASELINE config 5, the grid of
+    experiments/sensitivity_analysis.py:117-183): every object gets exactly what its own `fit(max_iter, tolerance,
+    verbose=False)` would give it -- history appended, state updated, per-fit early stop (base.py:183-203) -- but the
+    fits run concurrently on one GPU.  Returns the list of histories."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("tame_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    vis = list(vis)
+    if not vis:
+        return []
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    nf = len(vis)
+    f64 = torch.float64
+    cfgs = (_lib.TameConfig * nf)()
+    Yp, Mp, Cp = (C.c_void_p * nf)(), (C.c_void_p * nf)(), (C.c_void_p * nf)()
+    keep = []
+    for f, vi in enumerate(vis):
+        if vi.r < 1 or vi.r > _lib.MAX_R:
+            raise ValueError(f"latent_dim={vi.r} is outside the supported range 1..{_lib.MAX_R}")
+        vi._pull()
+        if vi._engine is not None:            # the batch call works on its own device copies
+            vi._engine.close()
+            vi._engine = None
+        cfg, kk = _fit_config(vi, dev.index)
+        Y = (vi.Y if vi.Y is not None else vi.model.Y).detach().to(dev, f64).contiguous()
+        Xm = vi._host_mean.detach().to(dev, f64).contiguous()
+        Xc = vi._host_cov.detach().to(dev, f64).contiguous()
+        cfgs[f] = cfg
+        Yp[f], Mp[f], Cp[f] = Y.data_ptr(), Xm.data_ptr(), Xc.data_ptr()
+        keep.append((kk, Y, Xm, Xc))
+    torch.cuda.synchronize(dev)
+    el = np.zeros((nf, max(max_iter, 1)))
+    ms = np.zeros((nf, max(max_iter, 1)))
+    nd = (C.c_int32 * nf)()
+    with torch.cuda.device(dev):
+        _lib.check(lib.tame_fit_batch(nf, cfgs, Yp, Mp, Cp, int(max_iter), float(tolerance), _lib.dptr(el), _lib.dptr(ms), nd, int(n_streams)))
+        torch.cuda.synchronize(dev)
+    out = []
+    for f, vi in enumerate(vis):
+        k = int(nd[f])
+        vi.history["elbo"].extend(float(x) for x in el[f, :k])
+        vi.history["reconstruction_error"].extend(float(x) for x in ms[f, :k])
+        vi._host_mean = keep[f][2].to("cpu", vi._host_mean.dtype)
+        vi._host_cov = keep[f][3].to("cpu", vi._host_cov.dtype)
+        vi._host_newer = True
+        vi._device_newer = False
+        vi._cached = None
+        out.append(vi.history)
+    return out

@@ -7,7 +7,7 @@ loop reads (R, R_inv, Sigma, Psi, Phi, Q) and produce the synthetic observations
 Same-seed parity: `generate_data()` issues the same sequence of torch RNG draws as the reference
 (temporal_ame.py:187-216: one d-vector per node for X^0, one per (node, t>0), then one 2-vector per dyad i<j
 per time step, each as `loc + scale_tril @ randn`), so the same constructor arguments under the same torch
-default dtype give the same Y.  tests/test_models_host.py checks this against the golden fixtures.
+default dtype give the same Y.  tests/test_host.py (test_model_mirror_reproduces_reference_data) checks this against the golden fixtures.
 
 Inherited quirk: the reference passes `seed` positionally into the base class's `sigma`
 slot (static_ame.py:89 vs base.py:64-74), so the constructor always seeds torch with 42 regardless of

@@ -13,6 +13,7 @@ for p in (ROOT, PKG):
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["conftest_lr1", "conftest_lr001", "r3_rho08", "r1_T1", "r4_T2", "earlystop", "config1", "config2"]
+GOLDEN_LONG = ["config2_long"]       # BASELINE config 2, 50 iterations of every method (too slow for the literal-oracle loop)
 METHODS = ["naive", "good", "bad"]
 
 

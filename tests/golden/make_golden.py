@@ -52,6 +52,9 @@ CASES = {
     # BASELINE config 2 shape (three_way_conparison), truncated to a few iterations: the
     # reference needs ~5-10 s per iteration here
     "config2": (dict(n_nodes=50, n_time=20, latent_dim=2), 0.01, 4, 0.0),
+    # the same, 50 iterations of all three methods (~15 minutes of reference time): per-method ELBO-trace parity on
+    # BASELINE config 2 proper (experiments/three_way_conparison.py:122-179 runs 500 at this step size)
+    "config2_long": (dict(n_nodes=50, n_time=20, latent_dim=2), 0.01, 50, 0.0),
 }
 
 METHODS = {

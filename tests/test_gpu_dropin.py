@@ -103,3 +103,42 @@ def test_state_assignment_and_pickle_round_trip(temporal_data):
     e0 = vi._compute_elbo()
     vi._update_step()
     assert vi._compute_elbo() != e0 and torch.count_nonzero(vi.X_mean) > 0
+
+
+def test_fit_batch_equals_individual_fits():
+    """`fit_batch` (additive helper over tame_fit_batch, BASELINE config 5): every object ends up exactly where its own
+    `fit(max_iter, tolerance)` would have put it -- history (incl. the per-fit early stop of base.py:183-203) and state."""
+    from src.models import TemporalAMEModel
+    from src.inference import TemporalAMENaiveMFVI, TemporalAMEStructuredMFVI, fit_batch
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        def make():
+            vis = []
+            for (n, T, ar, rho) in [(10, 5, 0.8, 0.5), (24, 3, 0.5, 0.0), (70, 4, 0.9, 0.8), (33, 9, 0.6, 0.3)]:
+                model = TemporalAMEModel(n_nodes=n, n_time=T, latent_dim=2, ar_coefficient=ar, rho_dyadic=rho, seed=42)
+                model.generate_data()
+                vis.append(TemporalAMENaiveMFVI(model, learning_rate=0.01, seed=42))
+                vis.append(TemporalAMEStructuredMFVI(model, factorization="good", learning_rate=1e-5 if n == 10 else 0.01, seed=42))
+            return vis
+        a, b = make(), make()
+        for vi in a:
+            vi.fit(max_iter=12, tolerance=1.09e-3, verbose=False)
+        hist = fit_batch(b, max_iter=12, tolerance=1.09e-3)
+        assert len(hist) == len(b)
+        stopped = 0
+        for va, vb in zip(a, b):
+            ea, eb = np.array(va.history["elbo"]), np.array(vb.history["elbo"])
+            assert len(ea) == len(eb), "per-fit early stop differs"
+            stopped += len(ea) < 12
+            assert np.all(np.abs(ea - eb) <= 1e-9 * np.abs(ea))
+            ma, mb = np.array(va.history["reconstruction_error"]), np.array(vb.history["reconstruction_error"])
+            assert np.all(np.abs(ma - mb) <= 1e-9 * np.abs(ma))
+            assert torch.allclose(va.X_mean, vb.X_mean, rtol=1e-9, atol=1e-12)
+            assert torch.allclose(va.X_cov, vb.X_cov, rtol=1e-9, atol=1e-12)
+        assert stopped >= 1          # the tiny-step fit stops early in both paths
+        # a batch-fitted object keeps working like any other: continue it on its own
+        b[1].fit(max_iter=2, tolerance=0.0, verbose=False)
+        assert len(b[1].history["elbo"]) == len(a[1].history["elbo"]) + 2
+    finally:
+        torch.set_default_dtype(old)

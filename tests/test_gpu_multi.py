@@ -81,3 +81,34 @@ def test_two_rank_fit_matches_oracle(tmp_path, scheduler):
                           "127.0.0.1", "--master-port", str(port), str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert res.stdout.count("OK") == 2, res.stdout
+
+
+def test_drop_in_devices_keyword_matches_single_gpu():
+    """`TemporalAMEStructuredMFVI(model, devices=[0, 1])` (additive keyword): one process, one handle per
+    GPU, fused sweep with NVLink peer hand-over -- the same history and state as the single-GPU object at rel 1e-9."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "python-temporal-ame-svi_b200"))
+    from src.models import TemporalAMEModel
+    from src.inference import TemporalAMENaiveMFVI, TemporalAMEStructuredMFVI
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        model = TemporalAMEModel(n_nodes=128, n_time=6, latent_dim=2, ar_coefficient=0.8, rho_dyadic=0.5, seed=42)
+        model.generate_data()
+        for make in (lambda **kw: TemporalAMEStructuredMFVI(model, factorization="good", learning_rate=0.3, seed=42, **kw),
+                     lambda **kw: TemporalAMENaiveMFVI(model, learning_rate=0.3, seed=42, **kw)):
+            one, two = make(device="cuda:0"), make(devices=[0, 1])
+            h1 = one.fit(max_iter=3, tolerance=0.0, verbose=False)
+            h2 = two.fit(max_iter=3, tolerance=0.0, verbose=False)
+            e1, e2 = np.array(h1["elbo"]), np.array(h2["elbo"])
+            assert np.all(np.abs(e1 - e2) <= 1e-9 * np.abs(e1)), (e1, e2)
+            assert torch.allclose(one.X_mean, two.X_mean, rtol=1e-9, atol=1e-12)
+            assert torch.allclose(one.X_cov, two.X_cov, rtol=1e-9, atol=1e-12)
+        with pytest.raises(ValueError):
+            m2 = TemporalAMEModel(n_nodes=100, n_time=3, latent_dim=2, seed=42)
+            m2.generate_data()
+            TemporalAMEStructuredMFVI(m2, devices=[0, 1]).fit(max_iter=1, verbose=False)
+    finally:
+        torch.set_default_dtype(old)

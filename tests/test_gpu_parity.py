@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, METHODS, golden_constants, load_golden, rel_err
+from conftest import GOLDEN_CASES, GOLDEN_LONG, METHODS, golden_constants, load_golden, rel_err
 from oracle import tame_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -28,7 +28,7 @@ def _trace_ok(a, b, tol=TOL):
 
 
 @pytest.mark.parametrize("meth", METHODS)
-@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_LONG)
 def test_c_abi_fit_matches_reference_golden(case, meth):
     """tame_fit_host (host buffers in, host buffers out) on the reference's own Y and initial state."""
     from gpu_util import fit_host
@@ -295,3 +295,24 @@ def test_elbo_pass_variants_agree_with_oracle(shape, variant, monkeypatch):
         assert abs(got[1] - ref[0]) <= TOL * abs(ref[0]), (variant, asym, got[1], ref[0])
         mse = orc.reconstruction_mse(Yt, Xm, c)
         assert abs(got[5] - mse) <= TOL * abs(mse)
+
+
+@pytest.mark.parametrize("meth", ["good", "naive"])
+def test_hundred_sweeps_no_drift(meth, sweep_path):
+    """The chain carries its inverse by rank-2 Woodbury updates between refreshes (every TAME_REFRESH nodes); 100 sweeps on
+    a shape with several refresh windows and streaming sub-blocks must still sit on the oracle's literal Gauss-Seidel
+    schedule: whole ELBO / MSE traces and the final state at rel 1e-9."""
+    from gpu_util import fit_host
+    n, T, r, iters = 200, 12, 4, 100
+    c, Y, Xm, Xc = _random_problem(n, T, r, seed=77, rho=0.5)
+    lr, mode = 0.3, orc.MODE_OF[meth]
+    el, ms, Gm, Gc = fit_host(Y, Xm, Xc, c, lr, mode, iters)
+    Om, Oc = Xm.copy(), Xc.copy()
+    oel, oms = [], []
+    for _ in range(iters):
+        orc.sweep_fast(Y, Om, Oc, c, lr, mode)
+        oel.append(orc.elbo(Y, Om, Oc, c, mode))
+        oms.append(orc.reconstruction_mse(Y, Om, c))
+    assert rel_err(Gm, Om) < TOL, rel_err(Gm, Om)
+    assert rel_err(Gc, Oc) < TOL, rel_err(Gc, Oc)
+    assert _trace_ok(el, oel) and _trace_ok(ms, oms)

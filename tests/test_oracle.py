@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, METHODS, golden_constants, load_golden, rel_err
+from conftest import GOLDEN_CASES, GOLDEN_LONG, METHODS, golden_constants, load_golden, rel_err
 from oracle import tame_oracle as orc
 
 # rel 1e-9 is north_star's tolerance; the oracle is expected to sit far inside it.
@@ -51,6 +51,27 @@ def test_config2_first_iterations(meth):
     c = golden_constants(g)
     Xm, Xc = g[f"{meth}_init_mean"].copy(), g[f"{meth}_init_cov"].copy()
     el, ms = orc.fit(g["Y"], Xm, Xc, c, float(g["lr"]), orc.MODE_OF[meth], int(g["max_iter"]), 0.0)
+    assert np.all(np.abs(el - g[f"{meth}_elbo"]) <= TOL * np.abs(g[f"{meth}_elbo"]))
+    assert np.all(np.abs(ms - g[f"{meth}_mse"]) <= TOL * np.abs(g[f"{meth}_mse"]))
+    assert rel_err(Xm, g[f"{meth}_final_mean"]) < TOL
+    assert rel_err(Xc, g[f"{meth}_final_cov"]) < TOL
+
+
+@pytest.mark.parametrize("meth", METHODS)
+@pytest.mark.parametrize("case", GOLDEN_LONG)
+def test_config2_fifty_iterations(case, meth):
+    """BASELINE config 2 (three_way_conparison: n=50, T=20, r=2, lr 0.01), 50 iterations of every method: the whole ELBO
+    and MSE traces and the final state of the reference, against the oracle's BLAS-vectorised literal sweep."""
+    g = load_golden(case)
+    c = golden_constants(g)
+    mode = orc.MODE_OF[meth]
+    Xm, Xc = g[f"{meth}_init_mean"].copy(), g[f"{meth}_init_cov"].copy()
+    el, ms = [], []
+    for _ in range(int(g["max_iter"])):
+        orc.sweep_fast(g["Y"], Xm, Xc, c, float(g["lr"]), mode)
+        el.append(orc.elbo(g["Y"], Xm, Xc, c, mode))
+        ms.append(orc.reconstruction_mse(g["Y"], Xm, c))
+    el, ms = np.array(el), np.array(ms)
     assert np.all(np.abs(el - g[f"{meth}_elbo"]) <= TOL * np.abs(g[f"{meth}_elbo"]))
     assert np.all(np.abs(ms - g[f"{meth}_mse"]) <= TOL * np.abs(g[f"{meth}_mse"]))
     assert rel_err(Xm, g[f"{meth}_final_mean"]) < TOL
