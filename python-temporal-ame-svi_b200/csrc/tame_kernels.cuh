@@ -1267,24 +1267,45 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 // ------------------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(256) k_covblend(TameParams P) {
-    constexpr int D = 2 + 2 * R, DD = D * D;
-    const size_t total = (size_t)P.nloc * P.T * DD;
+    // one warp per (own node, t) block: the raw block goes through shared memory once (coalesced), the transposed partner
+    // of every element is read from there
+    constexpr int D = 2 + 2 * R, DD = D * D, DP = D + 1, NE = (DD + 31) / 32;
+    __shared__ double tile[8][D * DP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double lr = P.lr, om = 1.0 - P.lr;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t cell = idx / DD;
-        const int e = (int)(idx - cell * DD), row = e / D, col = e - row * D;
-        const int l = (int)(cell / P.T), t = (int)(cell - (size_t)l * P.T);
+    const long ncell = (long)P.nloc * P.T;
+    for (long cell = (long)blockIdx.x * 8 + warp; cell < ncell; cell += (long)gridDim.x * 8) {
+        const int l = (int)(cell / P.T), t = (int)(cell - (long)l * P.T);
         const int i = tame_grow(l, P.panel, P.world, P.rank);
-        const double* cr = P.Craw + cell * DD;
-        double cf;
-        if (P.mode == 0) cf = (row == col) ? __ldcs(cr + e) : 0.0;
-        else {
-            const bool masked = (P.mode == 2) && ((row < 2) != (col < 2));
-            cf = masked ? 0.0 : 0.5 * (__ldcs(cr + e) + __ldcs(cr + col * D + row));
-            if (row == col) cf += 1e-6;
+        const double* cr = P.Craw + (size_t)cell * DD;
+        double* xc = P.Xc + ((size_t)i * P.T + t) * DD;
+        double old[NE];
+#pragma unroll
+        for (int m = 0; m < NE; ++m) {
+            const int e = lane + 32 * m;
+            if (e < DD) {
+                const int row = e / D, col = e - row * D;
+                tile[warp][row * DP + col] = __ldcs(cr + e);
+                old[m] = xc[e];
+            }
         }
-        double* xc = P.Xc + ((size_t)i * P.T + t) * DD + e;
-        *xc = lr * cf + om * *xc;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < NE; ++m) {
+            const int e = lane + 32 * m;
+            if (e < DD) {
+                const int row = e / D, col = e - row * D;
+                double cf;
+                if (P.mode == 0) cf = (row == col) ? tile[warp][row * DP + col] : 0.0;
+                else {
+                    const bool masked = (P.mode == 2) && ((row < 2) != (col < 2));
+                    cf = masked ? 0.0 : 0.5 * (tile[warp][row * DP + col] + tile[warp][col * DP + row]);
+                    if (row == col) cf += 1e-6;
+                }
+                __stcs(xc + e, lr * cf + om * old[m]);
+            }
+        }
+        __syncwarp();
     }
 }
 

@@ -78,9 +78,9 @@ cudaError_t launch_chain(const TameParams& P, int i0, int i1, cudaStream_t st) {
 }
 
 void launch_covblend(const TameParams& P, cudaStream_t st) {
-    const size_t total = (size_t)P.nloc * P.T * (2 + 2 * R) * (2 + 2 * R);
-    if (total == 0) return;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)device_sms(current_device()) * 16);
+    const size_t cells = (size_t)P.nloc * P.T;
+    if (cells == 0) return;
+    const int blocks = (int)std::min<size_t>((cells + 7) / 8, (size_t)device_sms(current_device()) * 16);
     k_covblend<R><<<blocks, 256, 0, st>>>(P);
     tame_count_launch(1);
 }
