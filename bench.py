@@ -37,6 +37,7 @@ HYPER = dict(ar_coefficient=0.8, rho_additive=0.5, rho_multiplicative=0.3, rho_d
 LR = 0.01
 METRIC = "SMF-VI dyad-timesteps/sec (N^2*T per sweep; sweep + ELBO + MSE per step)"
 UNIT = "dyad-timesteps/s"
+PANEL = int(os.environ.get("TAME_PANEL", "64"))    # nodes per ownership panel of the multi-GPU fit (multiple of 64)
 CPU_SAMPLE_NODES = 384      # fixed node subsample of the workload timed on the host (cpu_baseline and --impl reference)
 
 
@@ -227,7 +228,7 @@ def config_dict(n, T, r, world, requested_n=None):
     requested_n = n if requested_n is None else requested_n
     workload = f"good SMF fit iteration, n={n} T={T} r={r}, lr={LR}" + ("" if n == requested_n else f" (n reduced from {requested_n}: HBM)")
     units = float(n) * n * T
-    par = f"node-sharded x{world} (64-node panels, cyclic" + (")" if world == 1 else (
+    par = f"node-sharded x{world} ({PANEL}-node panels, cyclic" + (")" if world == 1 else (
         ", panel scheduler + NCCL broadcasts)" if os.environ.get("TAME_SWEEP") == "panel" else ", fused sweep with NVLink peer hand-over)"))
     return {"workload": workload, "n": n, "T": T, "r": r, "method": "good", "lr": LR, "parallelism": par,
             "l2": f"inputs larger than L2: each step streams Y twice ({2 * 16.0 * units / world / 1e9:.1f} GB per GPU per step)"}
@@ -266,7 +267,7 @@ def make_cfg(lib_mod, c, n, T, r, device, world, rank):
     cfg.logdet_R, cfg.logdet_Q, cfg.logdet_S0 = float(c["logdet_R"]), float(c["logdet_Q"]), float(c["logdet_S0"])
     keep = [np.ascontiguousarray(c[k], dtype=np.float64) for k in ("Phi", "Q_inv", "S0_inv")]
     cfg.Phi, cfg.Qinv, cfg.S0inv = (lib_mod.dptr(a) for a in keep)
-    cfg.device, cfg.world, cfg.rank, cfg.panel = device, world, rank, 64
+    cfg.device, cfg.world, cfg.rank, cfg.panel = device, world, rank, PANEL
     return cfg, keep
 
 
@@ -345,7 +346,7 @@ def run_ours(args, shape):
     c = hyper_constants(n, T, r)
 
     X = gen_latents(c).to(dev)
-    rows = owned_rows(n, 64, world, rank)
+    rows = owned_rows(n, PANEL, world, rank)
     nloc = sum(b - a for a, b in rows)
     Y = torch.empty(nloc, n, T, 2, dtype=torch.float64, device=dev)
     Rflat = np.ascontiguousarray(c["R"].reshape(4))

@@ -426,7 +426,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = dalloc((void**)&h->cst, sizeof(double) * c.size());
     // column parts per streaming unit: split the (long) upper part so that the first sub-blocks are ready early
-    h->nparts = (n >= 2048) ? 4 : 1;
+    h->nparts = (n >= 512) ? 4 : (n >= 192 ? 2 : 1);
     if (const char* v = getenv("TAME_NPARTS")) h->nparts = std::max(1, std::min(TAME_MAX_PARTS, atoi(v)));
     if (e == cudaSuccess) e = dalloc((void**)&h->H, sizeof(double) * (size_t)nloc * T * 2 * cfg->r * h->nparts);
     if (e == cudaSuccess) e = dalloc((void**)&h->Craw, sizeof(double) * (size_t)nloc * T * d * d);

@@ -455,7 +455,10 @@ __device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rowb
 #define TAME_LA2 3           // same for the input warps of NH = 2 (an iteration is two nodes there)
 #define TAME_NINP 8          // depth of the helper -> chain mailbox (power of two, >= TAME_NL + 2)
 #define TAME_MR 16           // depth of the intra-CTA hand-over ring (self-validating slots; the global slot is the fallback)
-#define TAME_WMAX 96         // widest inline window (partners)
+// inline window of the fused sweep: the TAME_WBACK(NH) previous + the current 32-node sub-block are summed by the helpers,
+// everything older by the streaming CTAs.  The wide team can afford one more sub-block, which takes the streaming CTAs'
+// reaction to a group's final release (one 32-column pass, ~15 us) off the chain's critical path.
+#define TAME_WBACK(NH) ((NH) == 1 ? 2 : 3)
 #define TAME_WATCHDOG_NS 4000000000ull
 enum { TAME_ROLE_ALL = 0, TAME_ROLE_TOTALS = 1, TAME_ROLE_INPUT = 2 };
 
@@ -463,9 +466,11 @@ template <int R, int NH>
 struct __align__(16) TameChainSmem {
     static constexpr int D = 2 + 2 * R, NV = 2 * R, TOT = TameTot<R>::TOT, DP = D + 1;
     static constexpr int NSLOT = (NH == 1) ? 8 : 16;   // staging ring of the input side (power of two)
+    static constexpr int WMAX = 32 * (TAME_WBACK(NH) + 1);          // widest inline window (partners)
+    static constexpr int RING = (NH == 1) ? TAME_RING : 2 * TAME_RING;   // rows of the z ring (>= WMAX + look-ahead, power of two)
     static constexpr int NTS = (NH == 1) ? 1 : 8;      // staging ring of the totals warp (NH = 2)
     struct Stage {                                  // one node's global inputs (cp.async destinations, 16-byte aligned)
-        double2 ywin[TAME_WMAX];                    // Y[i, wlo + s, t, :] of the inline window
+        double2 ywin[WMAX];                    // Y[i, wlo + s, t, :] of the inline window
         double2 hand[D];                            // hand-over slot {new mean, tag} of (i, t-1); foreign nodes (NH = 1): of (i, t)
         double mold[D], mnext[D];                   // old means of (i,t) and (i,t+1)
         double H[TAME_MAX_PARTS][NV];               // static partner part (per column part)
@@ -480,13 +485,13 @@ struct __align__(16) TameChainSmem {
         double mold[D];
         double wl[TAME_NL][2];                      // (w0, w1) of the trailing partners: wl[q] <-> partner i-1-q
     };
-    double ring[TAME_RING][NV];                     // z = [V,U] (new) of the last TAME_RING nodes at this time step
+    double ring[RING][NV];                     // z = [V,U] (new) of the last TAME_RING nodes at this time step
     Stage st[NSLOT];
     TStage tst[NTS];
     double pcol[D * DP];                            // totals side -> chain at refresh nodes: the precision without the trailing partners
     double pdt[TAME_NINP][D];                       // totals side -> chain: diag(P) without the trailing partners (naive rule)
     Inp inp[TAME_NINP];
-    double2 wbuf[NH][TAME_WMAX];                    // (w0, w1) of the window, per input warp
+    double2 wbuf[NH][WMAX];                    // (w0, w1) of the window, per input warp
     double2 Fs[2][32];                              // F = M J' of the up-date / down-date, one row per lane
     double rowb[TAME_GJ_ROWB(D)];
     double hvec[D], mprev[NH][D], hin[NH][NV];
@@ -593,9 +598,9 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
     constexpr bool DO_TOT = (ROLE != TAME_ROLE_INPUT), DO_INP = (ROLE != TAME_ROLE_TOTALS);
     constexpr int STEP = (ROLE == TAME_ROLE_INPUT) ? NH : 1;
     constexpr int D = S::D, NV = S::NV, TOT = S::TOT, DP = S::DP;
-    constexpr int WSB = FUSED ? TAME_SB : TAME_WIN, WBACK = FUSED ? 2 : 0, NWS = FUSED ? 3 : 2;
+    constexpr int WSB = FUSED ? TAME_SB : TAME_WIN, WBACK = FUSED ? TAME_WBACK(NH) : 0, NWS = FUSED ? TAME_WBACK(NH) + 1 : 2;
     constexpr int NL = TAME_NL, LA = (NH == 1) ? TAME_LA : ((ROLE == TAME_ROLE_INPUT) ? TAME_LA2 : TAME_LA);
-    constexpr int SMASK = (DO_INP ? S::NSLOT : S::NTS) - 1, IMASK = TAME_NINP - 1, RMASK = TAME_RING - 1;
+    constexpr int SMASK = (DO_INP ? S::NSLOT : S::NTS) - 1, IMASK = TAME_NINP - 1, RMASK = S::RING - 1;
     const int T = P.T, c = lane, cc = min(c, D - 1);
     const bool act = c < D, has_prev = t > 0, has_next = t < T - 1;
     const bool multi = FUSED && P.npeers > 0;
@@ -1018,7 +1023,7 @@ template <int R, bool FUSED, int NH>
 __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSmem<R, NH>& sm, int lane, int t, int i0, int i1) {
     using S = TameChainSmem<R, NH>;
     constexpr int D = S::D, NV = S::NV, DP = S::DP;
-    constexpr int NL = TAME_NL, IMASK = TAME_NINP - 1, RMASK = TAME_RING - 1;
+    constexpr int NL = TAME_NL, IMASK = TAME_NINP - 1, RMASK = S::RING - 1;
     const int T = P.T, c = lane, cc = min(c, D - 1);
     const bool act = c < D, has_next = t < T - 1;
     const bool multi = FUSED && P.npeers > 0;
@@ -1367,7 +1372,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
             yrow[rr] = P.Y + ((size_t)tame_lrow(min(k, P.n - 1), P.panel, P.world) * P.n * P.T + (tv ? t : 0)) * 2;
         }
         // optional trace of the unit (sub-block, slice 0, part 0): claim, upper part done, group 0 urgent, group 0 stamped
-        unsigned long long* utr = (P.trace != nullptr && slice == 0 && part == 0 && tid == 0) ? P.trace + 2 * nsb + 4 * lsb : nullptr;
+        unsigned long long* utr = (P.trace != nullptr && slice == 0 && part == P.nparts - 1 && tid == 0) ? P.trace + 2 * nsb + 4 * lsb : nullptr;
         if (utr) utr[0] = tame_globaltimer();
         // (a) static upper part: this part's share of the columns j > k
         {
@@ -1394,10 +1399,15 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
         // advance together (one full-width pass per release); a group whose final columns are out goes alone (the other
         // lanes are masked), writes its part of H and is stamped separately -- its chain warps wait for nothing else.
         if (utr) utr[1] = tame_globaltimer();
-        const int lowend = (part == 0) ? max(0, (sb - 2) * TAME_SB) : 0;
+        // the lower columns [0, (sb - WBACK) * 32) are dealt to the unit's column parts in contiguous 32-aligned ranges
+        // [lowbeg, lowend): a late sub-block's backlog (everything the chain released before the unit was claimed) is
+        // worked off by all parts in parallel; the last part carries the final release
+        const int lowall = max(0, (sb - TAME_WBACK(NH)) * TAME_SB);
+        const int lowq = ((lowall / TAME_SB + P.nparts - 1) / P.nparts) * TAME_SB;
+        const int lowbeg = min(lowall, part * lowq), lowend = min(lowall, lowbeg + lowq);
         // CTA-uniform bookkeeping lives in shared memory (the accumulators own the registers): s_dg[g] = columns done by
         // group g, s_plan = {c0, c1, active mask} of the next pass; `stamped` is a bit mask
-        if (tid < TAME_NG) s_dg[tid] = (t0 + 8 * tid < P.T) ? 0 : lowend;
+        if (tid < TAME_NG) s_dg[tid] = (t0 + 8 * tid < P.T) ? lowbeg : lowend;
         int stamped = 0, spins = 0;
         __syncthreads();
         for (;;) {
@@ -1438,7 +1448,7 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
                 for (int o = 4; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
                 int tg[TAME_NG];
 #pragma unroll
-                for (int g = 0; g < TAME_NG; ++g) tg[g] = min(lowend, (__shfl_sync(0xffffffffu, v, 8 * g) / TAME_SB) * TAME_SB);
+                for (int g = 0; g < TAME_NG; ++g) tg[g] = min(lowend, max(lowbeg, (__shfl_sync(0xffffffffu, v, 8 * g) / TAME_SB) * TAME_SB));
                 if (lane == 0) {
                     if (++spins > TAME_SPIN_LIMIT / 8) atomicExch(P.abort_flag, 1);
                     int c0 = -1, c1 = 0, mask = 0;
