@@ -1033,10 +1033,8 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     const double R00 = P.p1 * rdetR, R11 = P.p0 * rdetR, R01 = -P.q * rdetR;      // R = (R^-1)^-1
     const unsigned long long magic = 0x5AFE000000000000ull + (unsigned long long)(unsigned)P.epoch;
     auto refresh_at = [&](int k) { return k == i0 || (k % TAME_REFRESH) == 0; };
-    TameOwn own_i, own_n;                                        // nodes i and i+1
+    TameOwn own_i;
     own_i.init(i0, P.panel, P.world);
-    own_n.init(i0, P.panel, P.world);
-    own_n.next(P.panel, P.world);
     auto is_mine = [&](const TameOwn& o) { return !multi || o.pw == P.rank; };
     // component c of x = [a,b,U,V] sits at zpos in z = [V,U]; its h entry takes w0 (U rows) or w1 (V rows)
     const int zc = (cc >= 2) ? cc - 2 : 0;                       // index of this lane's component in h[2:], H, hin, ring rows
@@ -1059,16 +1057,12 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     size_t xoff = ((size_t)i0 * T + t) * D + cc;
 
     bool prev_mine = true;
-    for (int i = i0; i < i1; ++i, xoff += nstride, own_i.next(P.panel, P.world), own_n.next(P.panel, P.world)) {
+    for (int i = i0; i < i1; ++i, xoff += nstride, own_i.next(P.panel, P.world)) {
         if (!is_mine(own_i)) { prev_mine = false; continue; }
         const bool refresh = refresh_at(i);
-        const bool do_down = (i + 1 < i1) && is_mine(own_n) && !refresh_at(i + 1);
         {
             const long long c0 = clock64();
             if (!tame_wait_smem(&sm.ready[i & IMASK], i, lane, P.abort_flag)) return;
-            const long long c1 = clock64();
-            if (do_down && !tame_wait_smem(&sm.ready[(i + 1) & IMASK], i + 1, lane, P.abort_flag)) return;
-            wait_next += clock64() - c1;
             if ((refresh || mode == 0) && !tame_wait_smem(&sm.t_ready, i, lane, P.abort_flag)) return;
             // the trailing partners' ring rows: written by this warp, or -- foreign nodes with a separate totals warp -- awaited
             if (NH > 1 && !prev_mine && i > i0 && !tame_wait_smem(&sm.f_done, i - 1, lane, P.abort_flag)) return;
@@ -1117,16 +1111,38 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
             for (int k = 0; k < D; ++k) cw[k] = col[k];
             __syncwarp();
         } else {
-            // ---- up-date: node i-1 re-enters with its new mean
-            double z[NV];
-            const double2* zr = reinterpret_cast<const double2*>(sm.ring[(i - 1) & RMASK]);
+            // ---- P_i = P_{i-1} - G(z_i^old) + G(z_{i-1}^new): node i leaves with its old mean (pass 0), node i-1 re-enters with
+            // its new mean (pass 1).  One rolled loop: the rank-2 code exists once (instruction cache), the chain needs
+            // nothing of node i+1.
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                double z[NV];
+                if (pass == 0) {
+                    const double* mn = in.mold;
+                    if (R % 2 == 0) {
+                        const double2* mu2 = reinterpret_cast<const double2*>(mn + 2);          // U block
+                        const double2* mv2 = reinterpret_cast<const double2*>(mn + 2 + R);      // V block
 #pragma unroll
-            for (int x = 0; x < R; ++x) { const double2 v = zr[x]; z[2 * x] = v.x; z[2 * x + 1] = v.y; }
-            double f0, f1;
-            tame_rank2_F<R>(cw, z, f0, f1);
-            sm.Fs[0][lane] = make_double2(f0, f1);
-            __syncwarp();
-            tame_rank2_apply<R>(cw, z, f0, f1, sm.Fs[0], 1.0, R00, R01, R11);
+                        for (int x = 0; x < R / 2; ++x) {
+                            const double2 v = mv2[x], u = mu2[x];
+                            z[2 * x] = v.x; z[2 * x + 1] = v.y; z[R + 2 * x] = u.x; z[R + 2 * x + 1] = u.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < NV; ++x) z[x] = mn[tame_zidx<R>(x)];
+                    }
+                } else {
+                    const double2* zr = reinterpret_cast<const double2*>(sm.ring[(i - 1) & RMASK]);
+#pragma unroll
+                    for (int x = 0; x < R; ++x) { const double2 v = zr[x]; z[2 * x] = v.x; z[2 * x + 1] = v.y; }
+                }
+                double f0, f1;
+                tame_rank2_F<R>(cw, z, f0, f1);
+                __syncwarp();                                   // the previous pass has read Fs
+                sm.Fs[0][lane] = make_double2(f0, f1);
+                __syncwarp();
+                tame_rank2_apply<R>(cw, z, f0, f1, sm.Fs[0], pass == 0 ? -1.0 : 1.0, R00, R01, R11);
+            }
         }
         // ---- cw = raw C_i.  Mean (factorisation rule applied to the row), damped write, hand-over
         {
@@ -1180,29 +1196,9 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
                 }
             }
         }
-        // ---- down-date: node i+1 leaves with its old mean (independent of this node's mean: same instruction stream)
-        double zo[NV], g0 = 0.0, g1 = 0.0;
-        if (do_down) {
-            const double* mn = sm.inp[(i + 1) & IMASK].mold;
-            if (R % 2 == 0) {
-                const double2* mu2 = reinterpret_cast<const double2*>(mn + 2);          // U block
-                const double2* mv2 = reinterpret_cast<const double2*>(mn + 2 + R);      // V block
-#pragma unroll
-                for (int x = 0; x < R / 2; ++x) {
-                    const double2 v = mv2[x], u = mu2[x];
-                    zo[2 * x] = v.x; zo[2 * x + 1] = v.y; zo[R + 2 * x] = u.x; zo[R + 2 * x + 1] = u.y;
-                }
-            } else {
-#pragma unroll
-                for (int x = 0; x < NV; ++x) zo[x] = mn[tame_zidx<R>(x)];
-            }
-            tame_rank2_F<R>(cw, zo, g0, g1);
-            sm.Fs[1][lane] = make_double2(g0, g1);
-        }
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *((volatile int*)&sm.c_done) = i;
-        if (do_down) tame_rank2_apply<R>(cw, zo, g0, g1, sm.Fs[1], -1.0, R00, R01, R11);
         ++ncell;
         // progress is only consumed by the streaming CTAs, at sub-block granularity: one fence per 32 nodes
         if (((i + 1) % TAME_SB) == 0 || i + 1 == i1) {
