@@ -956,17 +956,28 @@ __device__ __forceinline__ void tame_chain_helper(const TameParams& P, TameChain
                 // trailing partners: the chain adds those)
                 if (P.mode == 0 && act)
                     sm.pdt[k & IMASK][c] = cdiag + ((c < 2) ? ((c == 0) ? P.p0 : P.p1) * m1 : ((c - 2 < R) ? P.p0 : P.p1) * gd);
-                if ((k == i0 || (k % TAME_REFRESH) == 0) && act) {
+                if (k == i0 || (k % TAME_REFRESH) == 0) {
+                    // refresh node: the precision without the trailing partners, from the running totals, inverted here
+                    // (in-place Gauss-Jordan); the chain warp re-enters the trailing partners by rank-2 up-dates
+                    double col[D];
                     const size_t cb = (size_t)(has_prev ? 1 : 0) * D * D;
                     double c0v, c1v;
-                    if (c < 2) { c0v = ((c == 0) ? P.p0 : P.q) * m1; c1v = ((c == 0) ? P.q : P.p1) * m1; }
+                    // the (a,b) block of P_obs is R^-1 times the partner count: the trailing partners' share is left out
+                    // here, their rank-2 up-dates in the chain warp bring it back
+                    const double m1r = m1 - (double)min(NL, k - i0);
+                    if (c < 2) { c0v = ((c == 0) ? P.p0 : P.q) * m1r; c1v = ((c == 0) ? P.q : P.p1) * m1r; }
                     else { c0v = sA * gy; c1v = sB * gy; }
 #pragma unroll
                     for (int q = 0; q < D; ++q) {
                         double v = (q == 0) ? c0v : (q == 1) ? c1v : ((q - 2 < R) ? sA : sB) * Gc[(DO_TOT && q >= 2) ? q - 2 : 0];
-                        v += P.cst[cb + q * D + c];
-                        if (has_next) v += P.cst[2 * D * D + q * D + c];
-                        sm.pcol[q * DP + c] = v;
+                        v += P.cst[cb + q * D + cc];
+                        if (has_next) v += P.cst[2 * D * D + q * D + cc];
+                        col[q] = act ? v : 0.0;
+                    }
+                    tame_gj_inverse<D, false>(col, sm.rowb, lane);
+                    if (act) {
+#pragma unroll
+                        for (int q = 0; q < D; ++q) sm.pcol[q * DP + c] = col[q];
                     }
                 }
             }
@@ -1086,64 +1097,47 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
         }
         if (act) sm.hvec[c] = hval;
 
+        // ---- the inverse.  Between refreshes P_i = P_{i-1} - G(z_i^old) + G(z_{i-1}^new): node i leaves with its old mean
+        // (pass 0), node i-1 re-enters with its new mean (pass 1).  At a refresh node the helper hands over the inverse of
+        // the precision without the trailing partners (built from the running totals, Gauss-Jordan) and passes 1..nle
+        // re-enter those partners.  One rolled loop: the rank-2 code exists once (instruction cache).
+        int pass = 0, pass_end = 2;
         if (refresh) {
-            // ---- precision column from the totals (helper) + the trailing partners' rank-2 terms, Gauss-Jordan
-            double col[D];
 #pragma unroll
-            for (int k = 0; k < D; ++k) col[k] = act ? sm.pcol[k * DP + c] : 0.0;
-            for (int q = 0; q < nle; ++q) {
-                const double* zr = sm.ring[(i - 1 - q) & RMASK];
-                const double zj = zr[zc];
-                const double g0c = (c == 0) ? 1.0 : ((c >= 2 && zc < R) ? zj : 0.0);      // g0 = (1,0,V,0)
-                const double g1c = (c == 1) ? 1.0 : ((c >= 2 && zc >= R) ? zj : 0.0);     // g1 = (0,1,0,U)
-                const double al = P.p0 * g0c + P.q * g1c, be = P.q * g0c + P.p1 * g1c;
-                if (act) {
-                    if (c >= 2) { col[0] += al; col[1] += be; }          // the (a,b) block already counts all n-1 partners
-#pragma unroll
-                    for (int x = 0; x < R; ++x) {
-                        col[2 + x] = fma(zr[x], al, col[2 + x]);
-                        col[2 + R + x] = fma(zr[R + x], be, col[2 + R + x]);
-                    }
-                }
-            }
-            tame_gj_inverse<D, false>(col, sm.rowb, lane);
-#pragma unroll
-            for (int k = 0; k < D; ++k) cw[k] = col[k];
-            __syncwarp();
-        } else {
-            // ---- P_i = P_{i-1} - G(z_i^old) + G(z_{i-1}^new): node i leaves with its old mean (pass 0), node i-1 re-enters with
-            // its new mean (pass 1).  One rolled loop: the rank-2 code exists once (instruction cache), the chain needs
-            // nothing of node i+1.
+            for (int k = 0; k < D; ++k) cw[k] = act ? sm.pcol[k * DP + c] : 0.0;
+            pass = 1;
+            pass_end = nle + 1;
+        }
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                double z[NV];
-                if (pass == 0) {
-                    const double* mn = in.mold;
-                    if (R % 2 == 0) {
-                        const double2* mu2 = reinterpret_cast<const double2*>(mn + 2);          // U block
-                        const double2* mv2 = reinterpret_cast<const double2*>(mn + 2 + R);      // V block
+        for (; pass < pass_end; ++pass) {
+            double z[NV];
+            if (pass == 0) {
+                const double* mn = in.mold;
+                if (R % 2 == 0) {
+                    const double2* mu2 = reinterpret_cast<const double2*>(mn + 2);          // U block
+                    const double2* mv2 = reinterpret_cast<const double2*>(mn + 2 + R);      // V block
 #pragma unroll
-                        for (int x = 0; x < R / 2; ++x) {
-                            const double2 v = mv2[x], u = mu2[x];
-                            z[2 * x] = v.x; z[2 * x + 1] = v.y; z[R + 2 * x] = u.x; z[R + 2 * x + 1] = u.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int x = 0; x < NV; ++x) z[x] = mn[tame_zidx<R>(x)];
+                    for (int x = 0; x < R / 2; ++x) {
+                        const double2 v = mv2[x], u = mu2[x];
+                        z[2 * x] = v.x; z[2 * x + 1] = v.y; z[R + 2 * x] = u.x; z[R + 2 * x + 1] = u.y;
                     }
                 } else {
-                    const double2* zr = reinterpret_cast<const double2*>(sm.ring[(i - 1) & RMASK]);
 #pragma unroll
-                    for (int x = 0; x < R; ++x) { const double2 v = zr[x]; z[2 * x] = v.x; z[2 * x + 1] = v.y; }
+                    for (int x = 0; x < NV; ++x) z[x] = mn[tame_zidx<R>(x)];
                 }
-                double f0, f1;
-                tame_rank2_F<R>(cw, z, f0, f1);
-                __syncwarp();                                   // the previous pass has read Fs
-                sm.Fs[0][lane] = make_double2(f0, f1);
-                __syncwarp();
-                tame_rank2_apply<R>(cw, z, f0, f1, sm.Fs[0], pass == 0 ? -1.0 : 1.0, R00, R01, R11);
+            } else {
+                const double2* zr = reinterpret_cast<const double2*>(sm.ring[(i - pass) & RMASK]);
+#pragma unroll
+                for (int x = 0; x < R; ++x) { const double2 v = zr[x]; z[2 * x] = v.x; z[2 * x + 1] = v.y; }
             }
+            double f0, f1;
+            tame_rank2_F<R>(cw, z, f0, f1);
+            __syncwarp();                                   // the previous pass has read Fs
+            sm.Fs[0][lane] = make_double2(f0, f1);
+            __syncwarp();
+            tame_rank2_apply<R>(cw, z, f0, f1, sm.Fs[0], pass == 0 ? -1.0 : 1.0, R00, R01, R11);
         }
+        __syncwarp();                                       // hvec
         // ---- cw = raw C_i.  Mean (factorisation rule applied to the row), damped write, hand-over
         {
             double h[D];
