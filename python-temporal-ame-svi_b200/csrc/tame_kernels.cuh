@@ -1063,6 +1063,11 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
     long long wait_in = 0, wait_next = 0;
     int ncell = 0;
     if (probe) dbg[0] = tame_globaltimer();
+    // the other ranks' hand-over buffers (kernel parameters -> registers: no indexed constant loads inside the node loop)
+    const int npeers = FUSED ? P.npeers : 0;
+    double2* peer[7];
+#pragma unroll
+    for (int pr = 0; pr < 7; ++pr) peer[pr] = P.hand_peer[pr];
     // running addresses of (i, t, c)
     const size_t nstride = (size_t)T * D;
     size_t xoff = ((size_t)i0 * T + t) * D + cc;
@@ -1169,7 +1174,9 @@ __device__ __forceinline__ void tame_chain_warp(const TameParams& P, TameChainSm
                     const double2 slotv = make_double2(mnew, __longlong_as_double((long long)tag));
                     __stcg(P.hand + xoff, slotv);
                     if (FUSED) {
-                        for (int pr = 0; pr < P.npeers; ++pr) __stcg(P.hand_peer[pr] + xoff, slotv);     // NVLink peer stores
+#pragma unroll
+                        for (int pr = 0; pr < 7; ++pr)
+                            if (pr < npeers) __stcg(peer[pr] + xoff, slotv);                            // NVLink peer stores
                     }
                 }
                 if (c >= 2) sm.ring[i & RMASK][zpos] = mnew;
