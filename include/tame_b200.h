@@ -109,6 +109,12 @@ int tame_iterate(tame_handle* h, double* out6_host);
 int tame_fit(tame_handle* h, int32_t max_iter, double tolerance, double* elbo_trace_host, double* mse_trace_host,
              int32_t* n_done);
 
+/* The whole loop of fit() on the DEVICE in one cooperative launch (k_fit: per iteration totals -> sweep -> covariance
+ * blend -> ELBO/MSE -> the stop rule of base.py:183-203, grid-wide barriers in between), asynchronous on the handle's
+ * stream: nothing returns to the host per iteration.  Traces / iteration count are written to DEVICE buffers
+ * (max_iter doubles each, one int32).  Single GPU, small problems (what tame_fit_batch queues for every fit). */
+int tame_fit_device(tame_handle* h, int32_t max_iter, double tolerance, double* elbo_trace_dev, double* mse_trace_dev,
+                    int32_t* n_done_dev);
 /* The same fit through HOST buffers: copies Y, X_mean, X_cov to the device, runs tame_fit, copies the state
  * back.  This is the end-to-end entry bench.py times (`e2e`).  Single GPU only. */
 int tame_fit_host(const tame_config* cfg, const double* Y_host, double* X_mean_host, double* X_cov_host,
@@ -119,9 +125,11 @@ int tame_fit_host(const tame_config* cfg, const double* Y_host, double* X_mean_h
  * and method): n_fits independent problems, each with its own tame_config and device buffers (Y_dev[f] is (n,n,T,2),
  * X_mean_dev[f] (n,T,d), X_cov_dev[f] (n,T,d,d), updated in place).  Traces are host arrays of n_fits * max_iter
  * doubles (row f = fit f); n_done[f] = iterations performed by fit f (early stop per fit, base.py:183-203).
- * Fits are independent Gauss-Seidel chains, so they run concurrently on `n_streams` CUDA streams (0 = default 8), each
- * driven by its own host thread inside the call (the caller's thread is one of them; the call returns when all fits
- * are done). */
+ * Fits are independent Gauss-Seidel chains.  Default path (single-GPU fits with n <= 1024 on one device): every fit is ONE
+ * cooperative launch of the whole-fit kernel (tame_fit_device: all iterations and the stop rule on the device), queued
+ * round-robin on `n_streams` CUDA streams (0 = default 16) from the calling thread, on pooled handles; the host only waits
+ * at the end.  Otherwise (or with TAME_BATCH=host): one host thread per stream runs the host-driven loop of tame_fit.
+ * The call returns when all fits are done. */
 int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* X_mean_dev,
                    double* const* X_cov_dev, int32_t max_iter, double tolerance, double* elbo_traces_host,
                    double* mse_traces_host, int32_t* n_done, int32_t n_streams);

@@ -22,6 +22,7 @@
 // ------------------------------------------------------------------------------------------------------
 // bookkeeping
 // ------------------------------------------------------------------------------------------------------
+static constexpr size_t FIT_PART_DOUBLES = 10 * 1024;   // (grid <= 1024 blocks) x (6 + 4) partial sums of k_fit
 static_assert(sizeof(tame_config) == 120, "tame_config layout is part of the ABI (ctypes mirror in _lib.py)");
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
@@ -110,6 +111,8 @@ struct tame_handle {
     TameParams P{};
     cudaStream_t stream = nullptr;
     bool y_bound = false, state_bound = false, y_symmetric = false;
+    bool skip_symcheck = false;          // tame_fit_batch's device-loop path: bind without the mirror check (and its sync)
+    double* fit_scratch = nullptr;       // k_fit: per-block partial sums, control block, barrier counter
     int* sym_flag = nullptr;
     int* cursor = nullptr;
     // device scratch
@@ -375,8 +378,8 @@ static int tame_reconfigure(tame_handle* h, const tame_config* cfg) {
     const std::vector<double> c = constant_block(cfg, h->d);
     h->cfg = *cfg;
     h->cfg.Phi = h->cfg.Qinv = h->cfg.S0inv = nullptr;
+    // `c` is pageable host memory: the runtime stages it before cudaMemcpyAsync returns, the copy itself is stream-ordered
     CK(cudaMemcpyAsync(h->cst, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));                        // `c` is pageable host memory on this stack
     TameParams& P = h->P;
     P.mode = cfg->mode;
     P.lr = cfg->lr;
@@ -448,6 +451,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     if (e == cudaSuccess) e = dalloc((void**)&h->hand, sizeof(double2) * (size_t)n * T * d);
     if (e == cudaSuccess) e = dalloc((void**)&h->unit_done, sizeof(int) * nunits * h->nparts * TAME_NG);
     if (e == cudaSuccess) e = dalloc((void**)&h->red6, sizeof(double) * 6);
+    if (e == cudaSuccess) e = dalloc((void**)&h->fit_scratch, sizeof(double) * (FIT_PART_DOUBLES + 8));
     if (e == cudaSuccess) e = dalloc((void**)&h->out6, sizeof(double) * 6);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->out6_pinned, sizeof(double) * 6);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->abort_pinned, sizeof(int));
@@ -497,7 +501,7 @@ int tame_destroy(tame_handle* h) {
     for (int k = 0; k < h->npeers; ++k) if (h->peer_base[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
     for (void* p : {(void*)h->Craw, (void*)h->H, (void*)h->hab, (void*)h->tot, (void*)h->tot_partial, (void*)h->cst, (void*)h->part_ll,
                     (void*)h->part_cell, (void*)h->red6, (void*)h->out6, (void*)h->progress, (void*)h->abort_flag,
-                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->trace, (void*)h->sym_flag, (void*)h->cursor})
+                    (void*)h->unit_counter, (void*)h->unit_done, (void*)h->hand, (void*)h->dbg, (void*)h->trace, (void*)h->fit_scratch, (void*)h->sym_flag, (void*)h->cursor})
         if (p) cudaFree(p);
     if (h->out6_pinned) cudaFreeHost(h->out6_pinned);
     if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
@@ -531,6 +535,7 @@ int tame_bind_Y(tame_handle* h, const double* Y) {
     // mirror property of Y (single GPU): lets the ELBO/MSE pass stream only the i<j half.  TAME_SYMMETRIC=0 disables.
     h->y_symmetric = false;
     const char* sv = getenv("TAME_SYMMETRIC");
+    if (h->skip_symcheck) { h->y_bound = true; return TAME_OK; }
     if (h->P.world == 1 && !(sv && atoi(sv) == 0)) {
         CK(cudaMemsetAsync(h->sym_flag, 0, sizeof(int), h->stream));
         k_symcheck<<<grid, block, 0, h->stream>>>(h->P, h->sym_flag);
@@ -688,6 +693,95 @@ int tame_fit(tame_handle* h, int32_t max_iter, double tolerance, double* elbo_tr
     return TAME_OK;
 }
 
+int tame_fit_device(tame_handle* h, int32_t max_iter, double tolerance, double* elbo_dev, double* mse_dev, int32_t* n_done_dev) {
+    if (!h || !elbo_dev || !mse_dev || !n_done_dev) return fail(TAME_EINVAL, "null argument");
+    if (!h->y_bound || !h->state_bound) return fail(TAME_ESTATE, "tame_fit_device before tame_bind_Y/tame_bind_state");
+    if (h->P.world != 1 || !h->fused) return fail(TAME_EINVAL, "tame_fit_device needs the single-GPU fused sweep");
+    if (max_iter <= 0) return fail(TAME_EINVAL, "max_iter must be positive");
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->ops->fit_grid(h->P) > 1024) return fail(TAME_EINVAL, "problem too large for the whole-fit kernel");
+    cudaStream_t st = h->stream;
+    CK(cudaMemsetAsync(h->fit_scratch + FIT_PART_DOUBLES, 0, sizeof(double) * 8, st));      // ctl[0..2], barrier counter
+    CK(cudaMemsetAsync(n_done_dev, 0, sizeof(int32_t), st));
+    TameFitArgs F;
+    F.max_iter = max_iter;
+    F.tolerance = tolerance;
+    F.logdetS0 = h->cfg.logdet_S0; F.logdetQ = h->cfg.logdet_Q; F.logdetR = h->cfg.logdet_R;
+    F.elbo_trace = elbo_dev; F.mse_trace = mse_dev; F.n_done = n_done_dev;
+    F.part = h->fit_scratch;
+    F.ctl = h->fit_scratch + FIT_PART_DOUBLES;
+    F.bar = reinterpret_cast<unsigned int*>(h->fit_scratch + FIT_PART_DOUBLES + 4);
+    h->P.epoch = h->epoch;               // iteration `it` of the kernel stamps with epoch + it + 1
+    cudaError_t e = h->ops->fit_device(h->P, F, nullptr, st);
+    h->epoch += max_iter;
+    h->P.epoch = h->epoch;
+    if (e != cudaSuccess) return fail(TAME_ECUDA, "whole-fit kernel launch: %s", cudaGetErrorString(e));
+    return TAME_OK;
+}
+
+// tame_fit_batch, device-loop path: every fit is ONE cooperative launch of k_fit (all its iterations and its stop rule on
+// the device), queued round-robin on a few streams from this one host thread; nothing comes back to the host until the end.
+static int fit_batch_device(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* Xm_dev,
+                            double* const* Xc_dev, int32_t max_iter, double tolerance, double* elbo_traces, double* mse_traces,
+                            int32_t* n_done, int32_t n_streams) {
+    const int S = std::max(1, std::min(n_streams <= 0 ? 16 : n_streams, n_fits));
+    const int dev0 = cfgs[0].device;
+    CK(cudaSetDevice(dev0));
+    std::vector<cudaStream_t> streams(S, nullptr);
+    std::vector<std::vector<tame_handle*>> pool(S);
+    double *el_d = nullptr, *ms_d = nullptr;
+    int32_t* nd_d = nullptr;
+    int rc = TAME_OK;
+    auto cleanup = [&]() {
+        std::string keep = g_err;
+        for (auto& v : pool) for (tame_handle* q : v) tame_destroy(q);
+        for (cudaStream_t s : streams) if (s) cudaStreamDestroy(s);
+        cudaFree(el_d); cudaFree(ms_d); cudaFree(nd_d);
+        g_err = keep;
+    };
+    cudaError_t e = cudaMalloc((void**)&el_d, sizeof(double) * (size_t)n_fits * max_iter);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ms_d, sizeof(double) * (size_t)n_fits * max_iter);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&nd_d, sizeof(int32_t) * (size_t)n_fits);
+    for (int s = 0; s < S && e == cudaSuccess; ++s) e = cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cleanup(); return fail(TAME_ENOMEM, "tame_fit_batch set-up: %s", cudaGetErrorString(e)); }
+    for (int f = 0; f < n_fits && rc == TAME_OK; ++f) {
+        const tame_config& cf = cfgs[f];
+        const int s = f % S;
+        tame_handle* h = nullptr;
+        for (tame_handle* q : pool[s])
+            if (q->cfg.n == cf.n && q->cfg.T == cf.T && q->cfg.r == cf.r) { h = q; break; }
+        if (h) rc = tame_reconfigure(h, &cf);
+        else {
+            rc = tame_create(&cf, &h);
+            if (rc == TAME_OK) { pool[s].push_back(h); rc = tame_set_stream(h, streams[s]); h->skip_symcheck = true; }
+        }
+        if (rc == TAME_OK) rc = tame_bind_Y(h, Y_dev[f]);
+        if (rc == TAME_OK) rc = tame_bind_state(h, Xm_dev[f], Xc_dev[f]);
+        if (rc == TAME_OK) rc = tame_fit_device(h, max_iter, tolerance, el_d + (size_t)f * max_iter, ms_d + (size_t)f * max_iter, nd_d + f);
+    }
+    for (int s = 0; s < S; ++s) {
+        cudaError_t es = cudaStreamSynchronize(streams[s]);
+        if (es != cudaSuccess && rc == TAME_OK) rc = fail(TAME_ECUDA, "tame_fit_batch: %s", cudaGetErrorString(es));
+    }
+    if (rc == TAME_OK) {
+        for (auto& v : pool)
+            for (tame_handle* q : v) {
+                int ab = 0;
+                cudaMemcpy(&ab, q->abort_flag, sizeof(int), cudaMemcpyDeviceToHost);
+                if (ab) rc = fail(TAME_EHANG, "the chain kernel's watchdog fired inside tame_fit_batch");
+            }
+    }
+    if (rc == TAME_OK) {
+        std::vector<double> tmp((size_t)n_fits * max_iter);
+        if (elbo_traces) { cudaMemcpy(tmp.data(), el_d, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost); memcpy(elbo_traces, tmp.data(), sizeof(double) * tmp.size()); }
+        if (mse_traces) { cudaMemcpy(tmp.data(), ms_d, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost); memcpy(mse_traces, tmp.data(), sizeof(double) * tmp.size()); }
+        e = cudaMemcpy(n_done, nd_d, sizeof(int32_t) * (size_t)n_fits, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(TAME_ECUDA, "tame_fit_batch read-back: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}
+
 int tame_fit_host(const tame_config* cfg, const double* Y_host, double* Xm_host, double* Xc_host, int32_t max_iter,
                   double tolerance, double* elbo_trace, double* mse_trace, int32_t* n_done) {
     if (!cfg || !Y_host || !Xm_host || !Xc_host) return fail(TAME_EINVAL, "null argument");
@@ -729,6 +823,17 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
     n_streams = std::min(n_streams, std::max(n_fits, 1));
     for (int f = 0; f < n_fits; ++f) n_done[f] = 0;
     if (max_iter <= 0 || n_fits == 0) return TAME_OK;
+    {
+        // small single-GPU fits on one device: the whole fit loop runs on the device, one launch per fit (TAME_BATCH=host
+        // keeps the host-driven loop below)
+        bool eligible = true;
+        for (int f = 0; f < n_fits; ++f)
+            eligible = eligible && cfgs[f].world == 1 && cfgs[f].n <= 1024 && cfgs[f].device == cfgs[0].device && cfgs[f].r >= 1 && cfgs[f].r <= TAME_MAX_R;
+        const char* v = getenv("TAME_BATCH");
+        const char* sw = getenv("TAME_SWEEP");
+        if (eligible && !(v && strcmp(v, "host") == 0) && !(sw && strcmp(sw, "panel") == 0))
+            return fit_batch_device(n_fits, cfgs, Y_dev, Xm_dev, Xc_dev, max_iter, tolerance, elbo_traces, mse_traces, n_done, n_streams);
+    }
     // Small fits are bound by the host's launch rate, not by the device: one host thread per stream, each taking the next
     // unstarted fit and running the loop of base.py:166-203 on its own handle and stream.  Kernels of different fits
     // overlap on the device; nothing is shared between the workers but the fit counter.

@@ -1268,15 +1268,15 @@ __device__ __forceinline__ void tame_chain_body(const TameParams& P, unsigned ch
 //   naive: rule = diag(1 / (diag(P) + 1e-8)), kept on the diagonal of the scratch     naive_mf.py:271-274, 280-282
 // ------------------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(256) k_covblend(TameParams P) {
+__device__ __forceinline__ void tame_covblend_impl(const TameParams& P, double* tile_all, int bid, int nb) {
     // one warp per (own node, t) block: the raw block goes through shared memory once (coalesced), the transposed partner
-    // of every element is read from there
+    // of every element is read from there.  tile_all: 8 * D * (D+1) doubles of shared memory.
     constexpr int D = 2 + 2 * R, DD = D * D, DP = D + 1, NE = (DD + 31) / 32;
-    __shared__ double tile[8][D * DP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* tile = tile_all + warp * (D * DP);
     const double lr = P.lr, om = 1.0 - P.lr;
     const long ncell = (long)P.nloc * P.T;
-    for (long cell = (long)blockIdx.x * 8 + warp; cell < ncell; cell += (long)gridDim.x * 8) {
+    for (long cell = (long)bid * 8 + warp; cell < ncell; cell += (long)nb * 8) {
         const int l = (int)(cell / P.T), t = (int)(cell - (long)l * P.T);
         const int i = tame_grow(l, P.panel, P.world, P.rank);
         const double* cr = P.Craw + (size_t)cell * DD;
@@ -1287,7 +1287,7 @@ __global__ void __launch_bounds__(256) k_covblend(TameParams P) {
             const int e = lane + 32 * m;
             if (e < DD) {
                 const int row = e / D, col = e - row * D;
-                tile[warp][row * DP + col] = __ldcs(cr + e);
+                tile[row * DP + col] = __ldcs(cr + e);
                 old[m] = xc[e];
             }
         }
@@ -1298,10 +1298,10 @@ __global__ void __launch_bounds__(256) k_covblend(TameParams P) {
             if (e < DD) {
                 const int row = e / D, col = e - row * D;
                 double cf;
-                if (P.mode == 0) cf = (row == col) ? tile[warp][row * DP + col] : 0.0;
+                if (P.mode == 0) cf = (row == col) ? tile[row * DP + col] : 0.0;
                 else {
                     const bool masked = (P.mode == 2) && ((row < 2) != (col < 2));
-                    cf = masked ? 0.0 : 0.5 * (tile[warp][row * DP + col] + tile[warp][col * DP + row]);
+                    cf = masked ? 0.0 : 0.5 * (tile[row * DP + col] + tile[col * DP + row]);
                     if (row == col) cf += 1e-6;
                 }
                 __stcs(xc + e, lr * cf + om * old[m]);
@@ -1309,6 +1309,12 @@ __global__ void __launch_bounds__(256) k_covblend(TameParams P) {
         }
         __syncwarp();
     }
+}
+template <int R>
+__global__ void __launch_bounds__(256) k_covblend(TameParams P) {
+    constexpr int D = 2 + 2 * R;
+    __shared__ double tile[8 * D * (D + 1)];
+    tame_covblend_impl<R>(P, tile, blockIdx.x, gridDim.x);
 }
 
 // stand-alone chain launch over one 64-node block (multi-GPU path); cooperative, grid = ceil(T/8)
@@ -1331,8 +1337,7 @@ __global__ void __launch_bounds__(2 * TAME_CHAIN_WPC * 32, 1) k_chain(TameParams
 // grid = n_chain_ctas + workers (all co-resident), block 256, dynamic smem = max of the two roles.
 // ------------------------------------------------------------------------------------------------------
 template <int R, int RW, int NH>
-__global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void tame_sweep_body(const TameParams& P, unsigned char* smem_raw) {
     static_assert(8 * RW == TAME_SB, "a streaming unit is one sub-block of rows");
     if ((int)blockIdx.x < P.n_chain_ctas) {
         tame_chain_body<R, true, NH>(P, smem_raw, blockIdx.x, 0, P.n);
@@ -1490,6 +1495,12 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
             __syncthreads();
         }
     }
+}
+
+template <int R, int RW, int NH>
+__global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tame_sweep_body<R, RW, NH>(P, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1859,54 +1870,59 @@ __global__ void __launch_bounds__(256, 1) k_llmse_mma(TameParams P, double* part
 // block 256 (8 warps); partial (gridDim.x, 4) = {lp0, lpt, ent, tr}.
 // ------------------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0, double logdetQ, double* partial) {
+struct TameCellSmem {
+    static constexpr int D = 2 + 2 * R;
+    double Cm[8][D * D];
+    double rowb[8][TAME_GJ_ROWB(D)];
+    double vec[8][2 * D];
+    double red[8][4];
+    double cT[3][D * D];      // S0inv, Qinv, Phi transposed: cT[m][k * D + c] = M[c][k]
+};
+template <int R>
+__device__ __forceinline__ void tame_cellterms_impl(const TameParams& P, double logdetS0, double logdetQ, double* partial,
+                                                    TameCellSmem<R>& sh, int bid, int nb) {
     constexpr int D = 2 + 2 * R, NE = (D * D + 31) / 32;
-    __shared__ double Cm[8][D * D];
-    __shared__ double rowb[8][TAME_GJ_ROWB(D)];
-    __shared__ double vec[8][2 * D];
-    __shared__ double red[8][4];
-    __shared__ double cT[3][D * D];      // S0inv, Qinv, Phi transposed: cT[m][k * D + c] = M[c][k]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < 3 * D * D; e += blockDim.x) {
         const int m = e / (D * D), rc = e % (D * D);
-        cT[m][(rc % D) * D + rc / D] = P.cst[(m == 2 ? 5 : m) * D * D + rc];
+        sh.cT[m][(rc % D) * D + rc / D] = P.cst[(m == 2 ? 5 : m) * D * D + rc];
     }
     __syncthreads();
     const double LOG2PI = 1.8378770664093454835606594728112;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const long ncell = (long)P.nloc * P.T;
-    for (long cell = (long)blockIdx.x * 8 + warp; cell < ncell; cell += (long)gridDim.x * 8) {
+    for (long cell = (long)bid * 8 + warp; cell < ncell; cell += (long)nb * 8) {
         const int l = (int)(cell / P.T), t = (int)(cell % P.T);
         const int i = tame_grow(l, P.panel, P.world, P.rank);
         const double* cp = P.Xc + ((size_t)i * P.T + t) * D * D;
 #pragma unroll
         for (int m = 0; m < NE; ++m) {
             int e = lane + 32 * m;
-            if (e < D * D) Cm[warp][e] = cp[e];
+            if (e < D * D) sh.Cm[warp][e] = cp[e];
         }
         const int c = lane;
         if (c < D) {
             double mt = P.Xm[((size_t)i * P.T + t) * D + c];
-            vec[warp][c] = mt;
-            vec[warp][D + c] = (t > 0) ? P.Xm[((size_t)i * P.T + t - 1) * D + c] : 0.0;
+            sh.vec[warp][c] = mt;
+            sh.vec[warp][D + c] = (t > 0) ? P.Xm[((size_t)i * P.T + t - 1) * D + c] : 0.0;
         }
         __syncwarp();
-        const double* A = cT[t == 0 ? 0 : 1];                 // S0inv or Qinv, A[k * D + c] = M[c][k]
-        const double* Phi = cT[2];
+        const double* A = sh.cT[t == 0 ? 0 : 1];                 // S0inv or Qinv, A[k * D + c] = M[c][k]
+        const double* Phi = sh.cT[2];
         double col[D];
         double tr = 0.0, trA = 0.0, resid = 0.0;
         if (c < D) {
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                col[k] = Cm[warp][k * D + c];
+                col[k] = sh.Cm[warp][k * D + c];
                 trA = fma(A[k * D + c], col[k], trA);       // sum_k A[c][k] * cov[k][c]
                 tr = (k == c) ? col[k] : tr;
             }
-            resid = vec[warp][c];
+            resid = sh.vec[warp][c];
             if (t > 0) {
                 double pm = 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) pm = fma(Phi[k * D + c], vec[warp][D + k], pm);
+                for (int k = 0; k < D; ++k) pm = fma(Phi[k * D + c], sh.vec[warp][D + k], pm);
                 resid -= pm;
             }
         } else {
@@ -1914,16 +1930,16 @@ __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0
             for (int k = 0; k < D; ++k) col[k] = 0.0;
         }
         __syncwarp();
-        if (c < D) vec[warp][c] = resid;
+        if (c < D) sh.vec[warp][c] = resid;
         __syncwarp();
         double quad = 0.0;
         if (c < D) {
             double a = 0.0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) a = fma(A[k * D + c], vec[warp][k], a);
+            for (int k = 0; k < D; ++k) a = fma(A[k * D + c], sh.vec[warp][k], a);
             quad = resid * a;
         }
-        const double logdet = tame_logdet_spd<D>(col, rowb[warp], lane);
+        const double logdet = tame_logdet_spd<D>(col, sh.rowb[warp], lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             tr += __shfl_xor_sync(0xffffffffu, tr, o);
@@ -1940,14 +1956,200 @@ __global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0
     }
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) red[warp][k] = acc[k];
+        for (int k = 0; k < 4; ++k) sh.red[warp][k] = acc[k];
     }
     __syncthreads();
     if (threadIdx.x < 4) {
-        double s = 0.0;
+        double sum = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+        for (int w = 0; w < 8; ++w) sum += sh.red[w][threadIdx.x];
+        partial[(size_t)bid * 4 + threadIdx.x] = sum;
+    }
+    __syncthreads();
+}
+template <int R>
+__global__ void __launch_bounds__(256) k_cellterms(TameParams P, double logdetS0, double logdetQ, double* partial) {
+    __shared__ TameCellSmem<R> sh;
+    tame_cellterms_impl<R>(P, logdetS0, logdetQ, partial, sh, blockIdx.x, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_fit: a WHOLE fit in one persistent cooperative launch (BASELINE config 5: many small independent fits) -- the loop of
+// src/inference/base.py:166-203 on the device: per iteration  totals -> sweep (chain + streaming CTAs, exactly k_sweep) ->
+// covariance blend -> ELBO / MSE partial sums -> reduction + the convergence test of base.py:183-203 by block 0, separated
+// by grid-wide barriers; the traces stay in device memory until the host asks for them.  No host involvement per iteration.
+// Meant for small n (the ELBO pass here is a plain one-warp-per-(row, time-slice) loop without the cp.async ring).
+// ------------------------------------------------------------------------------------------------------
+struct TameFitArgs {
+    int max_iter;
+    double tolerance, logdetS0, logdetQ, logdetR;
+    double* elbo_trace;       // device, max_iter
+    double* mse_trace;        // device, max_iter
+    int* n_done;              // device
+    double* part;             // device scratch: (grid, 6) partial sums {sq, quad, lp0, lpt, ent, tr}
+    double* ctl;              // device: [0] previous ELBO, [1] patience, [2] stop flag
+    unsigned int* bar;        // device: grid barrier counter (zero at launch)
+};
+
+__device__ __forceinline__ void tame_grid_sync(unsigned int* bar, unsigned int nblk, unsigned int& phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++phase;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const unsigned int target = phase * nblk;
+        while (*((volatile unsigned int*)bar) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// moment totals of the current means, one CTA per time step (strided), fixed summation order
+template <int R>
+__device__ __forceinline__ void tame_totals_small(const TameParams& P, int bid, int nb) {
+    constexpr int D = 2 + 2 * R, NV = 2 * R, TOT = TameTot<R>::TOT;
+    for (int t = bid; t < P.T; t += nb) {
+        for (int e = threadIdx.x; e < TOT; e += blockDim.x) {
+            int xa, xb = -1;
+            if (e < NV) xa = tame_zidx<R>(e);
+            else { const int f = e - NV; xa = tame_zidx<R>(f / NV); xb = tame_zidx<R>(f % NV); }
+            double acc = 0.0;
+            for (int j = 0; j < P.n; ++j) {
+                const double* m = P.Xm + ((size_t)j * P.T + t) * D;
+                const double va = __ldcg(m + xa);
+                acc += (xb < 0) ? va : va * __ldcg(m + xb);
+            }
+            P.tot[(size_t)t * TOT + e] = acc;
+        }
+    }
+}
+
+// quadratic form of the expected log-likelihood (i<j) + squared reconstruction error (i != j): one warp per (row, 32-step
+// time slice), lane <-> t, partners in order (structured_mf.py:124-146, temporal_ame.py:255-291); per-block sums -> part[bid][0..1]
+template <int R>
+__device__ __forceinline__ void tame_llmse_small(const TameParams& P, double* part, double* red /* 16 doubles smem */, int bid, int nb) {
+    constexpr int D = 2 + 2 * R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nslices = (P.T + 31) / 32;
+    const long nitems = (long)P.n * nslices;
+    double sq = 0.0, quad = 0.0;
+    for (long item = (long)bid * 8 + warp; item < nitems; item += (long)nb * 8) {
+        const int i = (int)(item / nslices), t = (int)(item - (long)i * nslices) * 32 + lane;
+        if (t < P.T) {
+            const double* mi = P.Xm + ((size_t)i * P.T + t) * D;
+            double ai = mi[0], bi = mi[1], Ui[R], Vi[R];
+#pragma unroll
+            for (int a = 0; a < R; ++a) { Ui[a] = mi[2 + a]; Vi[a] = mi[2 + R + a]; }
+            const double* yrow = P.Y + ((size_t)i * P.n * P.T + t) * 2;
+            double s = 0.0, q = 0.0;
+            // partners four at a time: the loads of a group are issued before the first use (L2 latency, no ring here)
+            for (int j0 = 0; j0 < P.n; j0 += 4) {
+                double2 y[4];
+                double rec[4][D];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = min(j0 + u, P.n - 1);
+                    y[u] = tame_ld_stream2(yrow + (size_t)j * P.T * 2);
+                    const double* mj = P.Xm + ((size_t)j * P.T + t) * D;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) rec[u][k] = __ldcg(mj + k);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u;
+                    if (j < P.n && j != i) {
+                        double d0 = ai + rec[u][1], d1 = rec[u][0] + bi;
+#pragma unroll
+                        for (int a = 0; a < R; ++a) { d0 = fma(Ui[a], rec[u][2 + R + a], d0); d1 = fma(rec[u][2 + a], Vi[a], d1); }
+                        const double e0 = y[u].x - d0, e1 = y[u].y - d1;
+                        s = fma(e0, e0, fma(e1, e1, s));
+                        if (j > i) q += P.p0 * e0 * e0 + 2.0 * P.q * e0 * e1 + P.p1 * e1 * e1;
+                    }
+                }
+            }
+            sq += s;
+            quad += q;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    }
+    if (lane == 0) { red[warp] = sq; red[8 + warp] = quad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += red[w]; b += red[8 + w]; }
+        part[(size_t)bid * 6 + 0] = a;
+        part[(size_t)bid * 6 + 1] = b;
+    }
+    __syncthreads();
+}
+
+template <int R, int RW, int NH>
+__global__ void __launch_bounds__(256, 1) k_fit(TameParams P0, TameFitArgs F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int D = 2 + 2 * R;
+    const unsigned int nblk = gridDim.x;
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    unsigned int phase = 0;
+    double* part4 = F.part + (size_t)nblk * 6;            // cell terms go through a (grid, 4) block of their own
+    for (int it = 0; it < F.max_iter; ++it) {
+        TameParams P = P0;
+        P.epoch = P0.epoch + it + 1;                       // stamps of this sweep (hand-over tags, unit_done)
+        // ---- running totals of the partner moments from the current means; reset of the sweep's counters
+        tame_totals_small<R>(P, bid, (int)nblk);
+        if (bid == 0) {
+            for (int t = tid; t < P.T; t += blockDim.x) P.progress[t] = 0;
+            if (tid == 0) *P.unit_counter = 0;
+        }
+        tame_grid_sync(F.bar, nblk, phase);
+        // ---- the sweep: chain CTAs + streaming CTAs, exactly as in k_sweep
+        tame_sweep_body<R, RW, NH>(P, smem_raw);
+        tame_grid_sync(F.bar, nblk, phase);
+        // ---- factorisation rule + damped write of the covariance blocks
+        tame_covblend_impl<R>(P, reinterpret_cast<double*>(smem_raw), bid, (int)nblk);
+        tame_grid_sync(F.bar, nblk, phase);
+        // ---- ELBO / MSE partial sums
+        tame_cellterms_impl<R>(P, F.logdetS0, F.logdetQ, part4, *reinterpret_cast<TameCellSmem<R>*>(smem_raw), bid, (int)nblk);
+        tame_llmse_small<R>(P, F.part, reinterpret_cast<double*>(smem_raw), bid, (int)nblk);
+        tame_grid_sync(F.bar, nblk, phase);
+        // ---- block 0: deterministic reduction, ELBO (k_finalize's formulas), the stop rule of base.py:183-203
+        if (bid == 0) {
+            double* red6 = reinterpret_cast<double*>(smem_raw);
+            if (tid < 6) {
+                double a = 0.0;
+                for (unsigned int b = 0; b < nblk; ++b) a += (tid < 2) ? F.part[(size_t)b * 6 + tid] : part4[(size_t)b * 4 + (tid - 2)];
+                red6[tid] = a;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const double LOG2PI = 1.8378770664093454835606594728112;
+                const double n = (double)P.n, npairs = 0.5 * n * (n - 1.0);
+                double ll = red6[1] + npairs * (double)P.T * (F.logdetR + 2.0 * LOG2PI);
+                if (P.mode != 0) ll += 0.1 * (P.p0 + P.p1) / (double)D * (n - 1.0) * red6[5];
+                ll *= -0.5;
+                const double elbo = ((ll + red6[2]) + red6[3]) + red6[4];
+                const double mse = red6[0] / (n * (n - 1.0) * (double)P.T);
+                F.elbo_trace[it] = elbo;
+                F.mse_trace[it] = mse;
+                *F.n_done = it + 1;
+                bool converged = false;
+                if (it > 0) {
+                    const double prev = F.ctl[0];
+                    const double rel = fabs(elbo - prev) / (fabs(prev) + 1e-8);
+                    const double pat = (rel < F.tolerance) ? F.ctl[1] + 1.0 : 0.0;
+                    F.ctl[1] = pat;
+                    converged = pat >= 3.0;
+                }
+                F.ctl[0] = elbo;
+                if (converged || *((volatile int*)P.abort_flag)) F.ctl[2] = 1.0;
+            }
+        }
+        tame_grid_sync(F.bar, nblk, phase);
+        if (*((volatile double*)&F.ctl[2]) != 0.0) break;
     }
 }
 
@@ -1961,6 +2163,8 @@ struct TameOps {
     cudaError_t (*chain)(const TameParams&, int i0, int i1, cudaStream_t);
     void (*covblend)(const TameParams&, cudaStream_t);
     cudaError_t (*sweep_fused)(const TameParams&, cudaStream_t);
+    cudaError_t (*fit_device)(const TameParams&, const TameFitArgs&, int* grid_out, cudaStream_t);
+    int (*fit_grid)(const TameParams&);
     int (*sweep_capacity)(int nh);
     int (*chain_max_T)();
     void (*llmse)(const TameParams&, double* partial, int* nblocks, int symmetric, cudaStream_t);

@@ -126,6 +126,58 @@ cudaError_t launch_sweep_nh(const TameParams& P, cudaStream_t st) {
     return cudaLaunchCooperativeKernel((void*)k_sweep<R, RW, NH>, dim3(p.n_chain_ctas + workers), dim3(256), args, sweep_smem_bytes<NH>(), st);
 }
 
+// grid of the fused sweep / whole-fit kernel for this problem: chain CTAs + streaming CTAs
+template <int NH>
+int sweep_grid_nh(const TameParams& P, int capacity, int* chain_ctas) {
+    const int cc = (P.T + TameTeam<NH>::TPC - 1) / TameTeam<NH>::TPC;
+    const int nunits = ((P.n + TAME_SB - 1) / TAME_SB) * ((P.T + 31) / 32) * P.nparts;
+    int workers = capacity - cc < nunits ? capacity - cc : nunits;
+    const long want = ((long)P.n * P.T + 1499) / 1500 + 2;
+    if ((long)workers > want) workers = (int)want;
+    *chain_ctas = cc;
+    return workers < 1 ? -1 : cc + workers;
+}
+
+// k_fit: the whole fit loop in one cooperative launch (small problems; tame_fit_batch)
+template <int NH>
+size_t fit_smem_bytes() {
+    const size_t a = sweep_smem_bytes<NH>(), b = sizeof(TameCellSmem<R>);
+    return a > b ? a : b;
+}
+template <int NH>
+int fit_capacity_nh() {
+    static PerDevice cap;
+    const int dev = current_device();
+    int c = cap.v[dev].load();
+    if (c < 0) {
+        int per = 0;
+        cudaFuncSetAttribute(k_fit<R, RW, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes<NH>());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_fit<R, RW, NH>, 256, fit_smem_bytes<NH>());
+        c = device_sms(dev) * per;
+        cap.v[dev].store(c);
+    }
+    return c;
+}
+template <int NH>
+cudaError_t launch_fit_nh(const TameParams& P, const TameFitArgs& F, int* grid_out, cudaStream_t st) {
+    TameParams p = P;
+    const int grid = sweep_grid_nh<NH>(P, fit_capacity_nh<NH>(), &p.n_chain_ctas);
+    if (grid < 0) return cudaErrorLaunchOutOfResources;
+    TameFitArgs f = F;
+    void* args[] = {(void*)&p, (void*)&f};
+    if (grid_out) *grid_out = grid;
+    tame_count_launch(1);
+    return cudaLaunchCooperativeKernel((void*)k_fit<R, RW, NH>, dim3(grid), dim3(256), args, fit_smem_bytes<NH>(), st);
+}
+int pick_nh(const TameParams& P);
+cudaError_t launch_fit_device(const TameParams& P, const TameFitArgs& F, int* grid_out, cudaStream_t st) {
+    return pick_nh(P) == 2 ? launch_fit_nh<2>(P, F, grid_out, st) : launch_fit_nh<1>(P, F, grid_out, st);
+}
+int fit_grid(const TameParams& P) {
+    int cc = 0;
+    return pick_nh(P) == 2 ? sweep_grid_nh<2>(P, fit_capacity_nh<2>(), &cc) : sweep_grid_nh<1>(P, fit_capacity_nh<1>(), &cc);
+}
+
 // Team shape: the wide team (NH = 2) needs twice the chain CTAs; it pays when the chain, not the streaming, bounds the
 // sweep -- several GPUs (the streaming shrinks with the rank count, the chain does not) or a small problem -- and
 // when enough SMs are left for the streaming CTAs.  TAME_NH=1|2 overrides.
@@ -220,5 +272,5 @@ void launch_cellterms(const TameParams& P, double logdetS0, double logdetQ, doub
 #define TAME_CAT2(a, b) a##b
 #define TAME_CAT(a, b) TAME_CAT2(a, b)
 extern const TameOps TAME_CAT(tame_ops_r, TAME_R) = {
-    R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, launch_covblend, launch_sweep_fused, sweep_capacity, chain_max_T,
+    R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, launch_covblend, launch_sweep_fused, launch_fit_device, fit_grid, sweep_capacity, chain_max_T,
     launch_llmse, launch_cellterms, llmse_blocks};

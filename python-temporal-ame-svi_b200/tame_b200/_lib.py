@@ -50,6 +50,7 @@ SIGNATURES = {
     "tame_elbo_mse": (C.c_int, [_P, _DP]),
     "tame_iterate": (C.c_int, [_P, _DP]),
     "tame_fit": (C.c_int, [_P, C.c_int32, C.c_double, _DP, _DP, C.POINTER(C.c_int32)]),
+    "tame_fit_device": (C.c_int, [_P, C.c_int32, C.c_double, _P, _P, _P]),
     "tame_fit_host": (C.c_int, [C.POINTER(TameConfig), _P, _P, _P, C.c_int32, C.c_double, _DP, _DP, C.POINTER(C.c_int32)]),
     "tame_fit_batch": (C.c_int, [C.c_int32, C.POINTER(TameConfig), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int32,
                                 C.c_double, _DP, _DP, C.POINTER(C.c_int32), C.c_int32]),
