@@ -477,6 +477,8 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     P.p0 = cfg->Rinv[0]; P.p1 = cfg->Rinv[3]; P.q = 0.5 * (cfg->Rinv[1] + cfg->Rinv[2]);
     P.Craw = h->Craw; P.H = h->H; P.hab = h->hab; P.tot = h->tot; P.cst = h->cst; P.progress = h->progress; P.abort_flag = h->abort_flag;
     P.unit_counter = h->unit_counter; P.unit_done = h->unit_done; P.epoch = 0; P.n_chain_ctas = 0; P.hand = h->hand; P.dbg = h->dbg; P.trace = h->trace; P.nparts = h->nparts; P.cursor = h->cursor; P.npeers = 0;
+    P.deterministic = 0;
+    if (const char* v = getenv("TAME_DETERMINISTIC")) P.deterministic = atoi(v) ? 1 : 0;
     P.probe_t = T - 1;
     if (const char* v = getenv("TAME_PROBE_T")) P.probe_t = std::max(0, std::min(T - 1, atoi(v)));
     for (int k = 0; k < 7; ++k) P.hand_peer[k] = nullptr;

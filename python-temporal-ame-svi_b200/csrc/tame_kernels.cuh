@@ -60,6 +60,7 @@ struct TameParams {
     int nparts;               // column parts per streaming unit (H holds nparts slabs of nloc*T*2R partial sums)
     int n_chain_ctas;
     int probe_t;              // time step of the second probe slot (dbg[8..15]); default T-1
+    int deterministic;        // 1: fixed summation order of H (no convoy start: TAME_DETERMINISTIC=1), bitwise reproducible sweeps
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -1385,7 +1386,7 @@ __device__ __forceinline__ void tame_sweep_body(const TameParams& P, unsigned ch
             // partner-record chunk fetched from HBM by one CTA is L2-hot for the rest (the records are re-read by every
             // row tile: 151 MB at config 4, more than L2 can hold next to the Y stream)
             int start = jb;
-            if (je - jb > 64 * JC) {
+            if (je - jb > 64 * JC && !P.deterministic) {
                 if (tid == 0) s_val = *((volatile int*)(P.cursor + part));
                 __syncthreads();
                 const int cur = s_val;

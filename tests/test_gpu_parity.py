@@ -237,25 +237,35 @@ def test_device_generator_distribution_and_mirror():
     assert np.array_equal(part, Y[32:64])
 
 
-def test_fit_batch_matches_per_fit_oracle():
-    """BASELINE config 5 in miniature: a grid of independent small fits (n, T, ar, rho vary; naive and good) through
-    tame_fit_batch, each compared with the oracle's fit() including the per-fit early stop."""
+@pytest.mark.parametrize("path", ["device-loop", "device-loop-nh1", "host-loop"])
+def test_fit_batch_matches_per_fit_oracle(path, monkeypatch):
+    """BASELINE config 5 in miniature: a grid of independent small fits (n, T, r, ar, rho vary; all three methods) through
+    tame_fit_batch, each compared with the oracle's fit() including the per-fit early stop.  Default path: one launch of the
+    whole-fit kernel per fit (k_fit, both team shapes); TAME_BATCH=host: the host-driven loop."""
     import ctypes as C
     from gpu_util import make_config
     from tame_b200 import _lib
     lib = _lib.load()
-    grid = [(10, 5, 0.8, 0.5), (24, 8, 0.5, 0.0), (40, 3, 0.9, 0.8), (33, 12, 0.3, -0.3), (70, 4, 0.8, 0.5), (12, 20, 0.7, 0.2)]
+    monkeypatch.delenv("TAME_BATCH", raising=False)
+    monkeypatch.delenv("TAME_NH", raising=False)
+    if path == "host-loop":
+        monkeypatch.setenv("TAME_BATCH", "host")
+    elif path == "device-loop-nh1":
+        monkeypatch.setenv("TAME_NH", "1")
+    grid = [(10, 5, 0.8, 0.5, 2), (24, 8, 0.5, 0.0, 2), (40, 3, 0.9, 0.8, 2), (33, 12, 0.3, -0.3, 2), (70, 4, 0.8, 0.5, 2),
+            (12, 20, 0.7, 0.2, 2), (130, 7, 0.8, 0.5, 8), (96, 33, 0.6, 0.3, 3)]
     fits, keep = [], []
-    for k, (n, T, ar, rho) in enumerate(grid):
-        for meth in ("naive", "good"):
-            c, Y, Xm, Xc = _random_problem(n, T, 2, seed=300 + k, rho=rho, ar=ar)
+    for k, (n, T, ar, rho, r) in enumerate(grid):
+        for meth in (("naive", "good") if r == 2 else ("good", "bad")):
+            c, Y, Xm, Xc = _random_problem(n, T, r, seed=300 + k, rho=rho, ar=ar)
             fits.append((c, Y, Xm, Xc, meth))
-    nf, max_iter, tol, lr = len(fits), 12, 2e-2, 0.3
+    nf, max_iter, tol = len(fits), 12, 2e-2
     cfgs = (_lib.TameConfig * nf)()
     Yp, Mp, Cp = (C.c_void_p * nf)(), (C.c_void_p * nf)(), (C.c_void_p * nf)()
     dev = []
+    lr_of = lambda meth: 0.05 if meth == "bad" else 0.3
     for f, (c, Y, Xm, Xc, meth) in enumerate(fits):
-        cfg, kk = make_config(c, lr, orc.MODE_OF[meth])
+        cfg, kk = make_config(c, lr_of(meth), orc.MODE_OF[meth])
         keep.append(kk)
         cfgs[f] = cfg
         t = [torch.as_tensor(a, dtype=torch.float64).cuda().contiguous() for a in (Y, Xm, Xc)]
@@ -267,7 +277,7 @@ def test_fit_batch_matches_per_fit_oracle():
     stopped_early = 0
     for f, (c, Y, Xm, Xc, meth) in enumerate(fits):
         Om, Oc = Xm.copy(), Xc.copy()
-        oel, oms = orc.fit(Y, Om, Oc, c, lr, orc.MODE_OF[meth], max_iter, tol)
+        oel, oms = orc.fit(Y, Om, Oc, c, lr_of(meth), orc.MODE_OF[meth], max_iter, tol, blocked=(c["n"] > 80))
         assert nd[f] == len(oel), (f, nd[f], len(oel))
         stopped_early += len(oel) < max_iter
         assert _trace_ok(el[f, :nd[f]], oel) and _trace_ok(ms[f, :nd[f]], oms)
@@ -316,3 +326,15 @@ def test_hundred_sweeps_no_drift(meth, sweep_path):
     assert rel_err(Gm, Om) < TOL, rel_err(Gm, Om)
     assert rel_err(Gc, Oc) < TOL, rel_err(Gc, Oc)
     assert _trace_ok(el, oel) and _trace_ok(ms, oms)
+
+
+def test_deterministic_mode_is_bitwise_reproducible(monkeypatch):
+    """TAME_DETERMINISTIC=1 fixes the summation order of the streamed partner sums (no convoy start position): two runs of the
+    same fit give bit-identical traces and state (the default order depends on timing at the 1e-16 level)."""
+    from gpu_util import fit_host
+    monkeypatch.setenv("TAME_DETERMINISTIC", "1")
+    c, Y, Xm, Xc = _random_problem(700, 5, 2, seed=5, rho=0.4)
+    a = fit_host(Y, Xm, Xc, c, 0.3, orc.GOOD, 3)
+    b = fit_host(Y, Xm, Xc, c, 0.3, orc.GOOD, 3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
