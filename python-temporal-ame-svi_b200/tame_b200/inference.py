@@ -311,6 +311,8 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
         self._engine: Optional[_Engine] = None
         self._host_mean: Optional[torch.Tensor] = None
         self._host_cov: Optional[torch.Tensor] = None
+        self._exact = None             # (X_mean, X_cov) FP64 copies of the device state behind the handed-out tensors
+        self._versions = None          # torch in-place version counters of the handed-out tensors at read-back time
         self._device_newer = False     # device state has moved on since the last read-back
         self._host_newer = False       # host tensors were (re)assigned since the last upload
         self._cached = None            # (elbo parts, mse) of the current device state
@@ -319,8 +321,14 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
     # ---- state: host tensors with lazy device mirroring ------------------------------------------------
     def _pull(self):
         if self._engine is not None and self._device_newer:
-            self._host_mean = self._engine.X_mean.to("cpu", self._host_mean.dtype)
-            self._host_cov = self._engine.X_cov.to("cpu", self._host_cov.dtype)
+            # the device state is FP64; the tensors handed to the caller keep the dtype the state was created in (float32 by
+            # default, like the reference).  The exact copy is what a later upload (pickle round trip, resumed fit) uses, unless
+            # the caller edited the handed-out tensors in place (their version counters tell).
+            m64, c64 = self._engine.X_mean.to("cpu"), self._engine.X_cov.to("cpu")
+            self._host_mean = m64.to(self._host_mean.dtype)
+            self._host_cov = c64.to(self._host_cov.dtype)
+            self._exact = (m64, c64)
+            self._versions = (self._host_mean._version, self._host_cov._version)
             self._device_newer = False
 
     @property
@@ -333,6 +341,7 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
         self._pull()
         self._host_mean = value
         self._host_newer = True
+        self._exact = None
 
     @property
     def X_cov(self) -> torch.Tensor:
@@ -344,6 +353,7 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
         self._pull()
         self._host_cov = value
         self._host_newer = True
+        self._exact = None
 
     def _ensure_engine(self) -> _Engine:
         if self._engine is None:
@@ -355,8 +365,16 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
             else:
                 self._engine = _Engine(self, self._devices[0] if self._devices else self._device)
             self._host_newer = True
-        if self._host_newer:
-            self._engine.upload(self._host_mean, self._host_cov)
+        edited = (self._versions is not None and not self._device_newer and
+                  (self._host_mean._version, self._host_cov._version) != self._versions)     # in-place edit of a handed-out tensor
+        if edited:
+            self._exact = None
+        if self._host_newer or edited:
+            if self._exact is not None:
+                self._engine.upload(*self._exact)          # bit-exact continuation (unpickled / re-created engine)
+            else:
+                self._engine.upload(self._host_mean, self._host_cov)
+            self._versions = (self._host_mean._version, self._host_cov._version)
             self._host_newer = False
             self._cached = None
         return self._engine
@@ -368,7 +386,13 @@ class BaseTemporalVariationalInference(BaseVariationalInference):
         state["_device_newer"] = False
         state["_host_newer"] = True
         state["_cached"] = None
+        state["_versions"] = None
         return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        if self._host_mean is not None:            # version counters restart with the new tensor objects
+            self._versions = (self._host_mean._version, self._host_cov._version)
 
     # ---- the three calls of the fit loop, on the device -------------------------------------------------
     def _update_step(self) -> None:
@@ -528,8 +552,9 @@ def fit_batch(vis, max_iter: int = 100, tolerance: float = 1e-4, device=None, n_
             vi._engine = None
         cfg, kk = _fit_config(vi, dev.index)
         Y = (vi.Y if vi.Y is not None else vi.model.Y).detach().to(dev, f64).contiguous()
-        Xm = vi._host_mean.detach().to(dev, f64).contiguous()
-        Xc = vi._host_cov.detach().to(dev, f64).contiguous()
+        src = vi._exact if (vi._exact is not None and vi._versions == (vi._host_mean._version, vi._host_cov._version)) else (vi._host_mean, vi._host_cov)
+        Xm = src[0].detach().to(dev, f64).contiguous()
+        Xc = src[1].detach().to(dev, f64).contiguous()
         cfgs[f] = cfg
         Yp[f], Mp[f], Cp[f] = Y.data_ptr(), Xm.data_ptr(), Xc.data_ptr()
         keep.append((kk, Y, Xm, Xc))
@@ -545,8 +570,11 @@ def fit_batch(vis, max_iter: int = 100, tolerance: float = 1e-4, device=None, n_
         k = int(nd[f])
         vi.history["elbo"].extend(float(x) for x in el[f, :k])
         vi.history["reconstruction_error"].extend(float(x) for x in ms[f, :k])
-        vi._host_mean = keep[f][2].to("cpu", vi._host_mean.dtype)
-        vi._host_cov = keep[f][3].to("cpu", vi._host_cov.dtype)
+        m64, c64 = keep[f][2].to("cpu"), keep[f][3].to("cpu")
+        vi._host_mean = m64.to(vi._host_mean.dtype)
+        vi._host_cov = c64.to(vi._host_cov.dtype)
+        vi._exact = (m64, c64)
+        vi._versions = (vi._host_mean._version, vi._host_cov._version)
         vi._host_newer = True
         vi._device_newer = False
         vi._cached = None

@@ -142,3 +142,24 @@ def test_fit_batch_equals_individual_fits():
         assert len(b[1].history["elbo"]) == len(a[1].history["elbo"]) + 2
     finally:
         torch.set_default_dtype(old)
+
+
+def test_resume_after_pickle_is_exact_and_in_place_edits_are_seen(temporal_data):
+    """The device state is FP64 while the handed-out tensors keep the reference's default dtype (float32): a pickled /
+    resumed fit continues from the exact state (same trace as an uninterrupted fit), and an in-place edit of `vi.X_mean`
+    -- the reference mutates its tensors in place -- reaches the device before the next sweep."""
+    from src.inference import TemporalAMEStructuredMFVI
+    model = temporal_data["model"]
+    a = TemporalAMEStructuredMFVI(model, factorization="good", learning_rate=0.3, seed=42)
+    ha = list(a.fit(max_iter=5, tolerance=0.0, verbose=False)["elbo"])
+    b = TemporalAMEStructuredMFVI(model, factorization="good", learning_rate=0.3, seed=42)
+    b.fit(max_iter=3, tolerance=0.0, verbose=False)
+    assert b.X_mean.dtype == torch.float32
+    c = pickle.loads(pickle.dumps(b))
+    hc = list(c.fit(max_iter=2, tolerance=0.0, verbose=False)["elbo"])
+    assert len(hc) == 5
+    assert np.all(np.abs(np.array(hc) - np.array(ha)) <= 1e-12 * np.abs(np.array(ha))), (hc, ha)
+    e0 = c._compute_elbo()
+    c.X_mean.mul_(0.5)                       # in place, on the tensor the property handed out
+    e1 = c._compute_elbo()
+    assert abs(e1 - e0) > 1e-6 * abs(e0)
