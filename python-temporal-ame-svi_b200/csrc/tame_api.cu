@@ -721,6 +721,7 @@ int tame_fit_device(tame_handle* h, int32_t max_iter, double tolerance, double* 
     return TAME_OK;
 }
 
+static constexpr int BATCH_FALLBACK = 1;      // internal: the device-loop path declined before doing any work
 // tame_fit_batch, device-loop path: every fit is ONE cooperative launch of k_fit (all its iterations and its stop rule on
 // the device), queued round-robin on a few streams from this one host thread; nothing comes back to the host until the end.
 static int fit_batch_device(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* Xm_dev,
@@ -757,6 +758,7 @@ static int fit_batch_device(int32_t n_fits, const tame_config* cfgs, const doubl
             rc = tame_create(&cf, &h);
             if (rc == TAME_OK) { pool[s].push_back(h); rc = tame_set_stream(h, streams[s]); h->skip_symcheck = true; }
         }
+        if (rc == TAME_OK && f == 0 && !h->fused) { cleanup(); return BATCH_FALLBACK; }   // no fused sweep at this shape: host loop
         if (rc == TAME_OK) rc = tame_bind_Y(h, Y_dev[f]);
         if (rc == TAME_OK) rc = tame_bind_state(h, Xm_dev[f], Xc_dev[f]);
         if (rc == TAME_OK) rc = tame_fit_device(h, max_iter, tolerance, el_d + (size_t)f * max_iter, ms_d + (size_t)f * max_iter, nd_d + f);
@@ -821,8 +823,6 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
                    double* const* Xc_dev, int32_t max_iter, double tolerance, double* elbo_traces, double* mse_traces,
                    int32_t* n_done, int32_t n_streams) {
     if (n_fits < 0 || (n_fits > 0 && (!cfgs || !Y_dev || !Xm_dev || !Xc_dev || !n_done))) return fail(TAME_EINVAL, "null argument");
-    if (n_streams <= 0) n_streams = 8;
-    n_streams = std::min(n_streams, std::max(n_fits, 1));
     for (int f = 0; f < n_fits; ++f) n_done[f] = 0;
     if (max_iter <= 0 || n_fits == 0) return TAME_OK;
     {
@@ -833,9 +833,13 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
             eligible = eligible && cfgs[f].world == 1 && cfgs[f].n <= 1024 && cfgs[f].device == cfgs[0].device && cfgs[f].r >= 1 && cfgs[f].r <= TAME_MAX_R;
         const char* v = getenv("TAME_BATCH");
         const char* sw = getenv("TAME_SWEEP");
-        if (eligible && !(v && strcmp(v, "host") == 0) && !(sw && strcmp(sw, "panel") == 0))
-            return fit_batch_device(n_fits, cfgs, Y_dev, Xm_dev, Xc_dev, max_iter, tolerance, elbo_traces, mse_traces, n_done, n_streams);
+        if (eligible && !(v && strcmp(v, "host") == 0) && !(sw && strcmp(sw, "panel") == 0)) {
+            const int rc = fit_batch_device(n_fits, cfgs, Y_dev, Xm_dev, Xc_dev, max_iter, tolerance, elbo_traces, mse_traces, n_done, n_streams);
+            if (rc != BATCH_FALLBACK) return rc;
+        }
     }
+    if (n_streams <= 0) n_streams = 8;
+    n_streams = std::min(n_streams, std::max(n_fits, 1));
     // Small fits are bound by the host's launch rate, not by the device: one host thread per stream, each taking the next
     // unstarted fit and running the loop of base.py:166-203 on its own handle and stream.  Kernels of different fits
     // overlap on the device; nothing is shared between the workers but the fit counter.
