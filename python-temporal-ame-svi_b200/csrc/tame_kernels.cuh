@@ -431,18 +431,20 @@ __device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rowb
 // Warp pair <-> time step t: a CHAIN warp and a HELPER warp walk the nodes in order.  For cell (i,t)
 //   P_i = const_t + sum_{j != i} G(z_j),  G(z) = J_z' R^-1 J_z (rank 2),  z_j = [V_j, U_j] at time t (new for j<i, old for j>i)
 //   C_i = P_i^-1 (then mask / symmetrise / jitter, :270-277),  mu = C_i h_i,  damped write (:282-287).
-// The only loop-carried work is the inverse: P_{i+1} = P_i - G(z_{i+1}^old) + G(z_i^new).  The chain warp carries the raw
-// inverse in registers (lane c <-> column c) and applies the two rank-2 Woodbury corrections per node (2x2 capacitance
-// matrix, one reciprocal each); the DOWN-date with node i+1's old mean does not depend on node i's result, so it is issued
-// in the same instruction stream as node i's mean (mu = C_i h_i) and overlaps it.  Every TAME_REFRESH nodes (and at the
-// first node after foreign nodes) the inverse is rebuilt from the running moment totals by an in-place Gauss-Jordan.
+// The only loop-carried work is the inverse: P_i = P_{i-1} - G(z_i^old) + G(z_{i-1}^new).  The chain warp carries the raw
+// inverse in registers (lane c <-> column c) and applies the two rank-2 Woodbury corrections (2x2 capacitance matrix, one
+// reciprocal each) at the start of the node in ONE rolled loop -- the code exists once (instruction cache) and the chain
+// needs nothing of node i+1.  Every TAME_REFRESH nodes (and at the first node after foreign nodes) the HELPER side rebuilds
+// the inverse from the running moment totals (in-place Gauss-Jordan) without the last TAME_NL partners, which the chain
+// re-enters by up-dates in the same loop.
 // Everything else is the helper's: ALL global loads TAME_LA nodes ahead (cp.async staging: the inline window's Y entries,
 // old means, the static partner part H, the hand-over slot of (i,t-1)), the inline window's partner sum, the AR(1) terms
 // with the NEW mean of (i,t-1) and the OLD mean of (i,t+1), the running totals, and -- multi-GPU -- the nodes of other ranks.
 // The chain warp stores its raw covariance column straight to the global scratch Craw; the factorisation rule, the
 // symmetrisation, the jitter and the damped write into X_cov happen in a streaming post-pass (k_covblend).
 // Mailboxes (shared memory):  helper -> chain  inp[k] {h without the last TAME_NL partners, old mean, those partners'
-// weights, diag(P)} + the precision column at refresh nodes (pcol);  chain -> helper  ring[k] (new z).
+// weights}, pdt[k] (diag(P), naive rule), pcol (the inverse at refresh nodes);  chain -> helper  ring[k] (new z), mring[k]
+// (new mean for the next time step's helper in the same CTA).
 // Counters: ready[slot] (inputs of the node in that mailbox slot), t_ready (totals-side data), f_done (foreign nodes),
 // c_done (chain).
 // Two shapes of the warp team per time step (template NH):
@@ -1331,9 +1333,10 @@ __global__ void __launch_bounds__(2 * TAME_CHAIN_WPC * 32, 1) k_chain(TameParams
 //   the remaining CTAs       are streaming workers.  A unit = (32-row sub-block sb, 32-step time slice).  A worker
 //       takes units in ascending order from an atomic counter, keeps the unit's 32 x 32 x 2R partner sums in
 //       registers, streams  (a) the static upper part j > k (partners still carrying their old means when row k
-//       is updated) immediately and (b) the lower columns j < (sb-2)*32 (new means) as the chain's progress
+//       is updated) immediately and (b) its share of the lower columns j < (sb-WBACK)*32 (new means) as the chain's progress
 //       counters release them, then writes H once (no read-modify-write, no atomics) and stamps unit_done.
-//   The chain waits for a sub-block's stamp before entering it and covers the last (up to) 96 partners inline.
+//   The chain's helpers wait for a sub-block's stamps (one per group of 8 time steps) before entering it and cover the last
+//   (up to) 96 / 128 partners (narrow / wide team) inline.
 // Every Y entry is read exactly once per sweep; the schedule is the reference's.
 // grid = n_chain_ctas + workers (all co-resident), block 256, dynamic smem = max of the two roles.
 // ------------------------------------------------------------------------------------------------------
