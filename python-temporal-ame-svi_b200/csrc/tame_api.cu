@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <thread>
@@ -120,6 +121,7 @@ struct tame_handle {
     double *part_ll = nullptr, *part_cell = nullptr, *red6 = nullptr, *out6 = nullptr;
     int *progress = nullptr, *abort_flag = nullptr, *unit_counter = nullptr, *unit_done = nullptr;
     int epoch = 0, nparts = 1;
+    int cap_n = 0, cap_T = 0;            // shape the buffers were sized for (tame_reconfigure accepts any n, T within it)
     bool fused = true, fused_multi = true;
     double2* hand = nullptr;
     void* peer_base[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // IPC mappings of the peers' hand buffers
@@ -367,15 +369,40 @@ static std::vector<double> constant_block(const tame_config* cfg, int d) {
     return c;
 }
 
-// Point an existing single-GPU handle at another fit of the SAME shape (n, T, r, device): new hyper-parameters, mode and
-// learning rate; Y and the state are bound afresh by the caller.  tame_fit_batch pools its handles with this (a handle is
-// ~20 device allocations, and cudaFree synchronises the whole device).
+// shape-dependent launch parameters of a handle (shared by tame_create and tame_reconfigure)
+static int shape_nparts(int n) {
+    int np = (n >= 512) ? 4 : (n >= 192 ? 2 : 1);
+    if (const char* v = getenv("TAME_NPARTS")) np = std::max(1, std::min(TAME_MAX_PARTS, atoi(v)));
+    return np;
+}
+static int shape_ns(int n) { return std::max(1, std::min(64, (n + 127) / 128)); }
+
+// Point an existing single-GPU handle at another fit with the same r and device and a shape (n, T) within the one its
+// buffers were sized for: new hyper-parameters, mode and learning rate; Y and the state are bound afresh by the caller.
+// tame_fit_batch pools its handles with this (a handle is ~25 device / pinned allocations -- milliseconds on the host, and
+// cudaFree synchronises the whole device).  Stale hand-over tags and unit stamps of earlier fits cannot be mistaken for
+// current ones: they carry the handle's epoch, which only grows.
 static int tame_reconfigure(tame_handle* h, const tame_config* cfg) {
-    if (cfg->n != h->cfg.n || cfg->T != h->cfg.T || cfg->r != h->cfg.r || cfg->device != h->cfg.device || cfg->world != 1 || h->P.world != 1)
-        return fail(TAME_EINVAL, "tame_reconfigure: shape mismatch");
+    if (cfg->r != h->cfg.r || cfg->device != h->cfg.device || cfg->world != 1 || h->P.world != 1)
+        return fail(TAME_EINVAL, "tame_reconfigure: latent dimension / device mismatch");
+    if (cfg->n < 2 || cfg->T < 1 || cfg->n > h->cap_n || cfg->T > h->cap_T)
+        return fail(TAME_EINVAL, "tame_reconfigure: shape (%d, %d) outside the handle's capacity (%d, %d)", cfg->n, cfg->T, h->cap_n, h->cap_T);
     if (cfg->mode < 0 || cfg->mode > 2) return fail(TAME_EINVAL, "unknown mode %d", cfg->mode);
     if (!cfg->Phi || !cfg->Qinv || !cfg->S0inv) return fail(TAME_EINVAL, "Phi/Qinv/S0inv must be given");
     const std::vector<double> c = constant_block(cfg, h->d);
+    if (cfg->n != h->P.n || cfg->T != h->P.T) {
+        const int n = cfg->n, T = cfg->T;
+        h->nloc = n;
+        h->NS = shape_ns(n);
+        h->nparts = shape_nparts(n);
+        h->P.n = n; h->P.T = T; h->P.nloc = n; h->P.nparts = h->nparts;
+        h->P.probe_t = T - 1;
+        if (const char* v = getenv("TAME_PROBE_T")) h->P.probe_t = std::max(0, std::min(T - 1, atoi(v)));
+        const char* v = getenv("TAME_SWEEP");
+        h->fused = !(v && strcmp(v, "panel") == 0) && (T + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC + 1 <= h->ops->sweep_capacity(1);
+        h->nb_ll = h->ops->llmse_blocks(h->P);
+        h->nb_cell = h->ops->cellterms_blocks(h->P);
+    }
     h->cfg = *cfg;
     h->cfg.Phi = h->cfg.Qinv = h->cfg.S0inv = nullptr;
     // `c` is pageable host memory: the runtime stages it before cudaMemcpyAsync returns, the copy itself is stream-ordered
@@ -424,13 +451,13 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     h->cfg.Phi = h->cfg.Qinv = h->cfg.S0inv = nullptr;             // host pointers are not retained
 
     const int TOT = h->ops->tot;
-    h->NS = std::max(1, std::min(64, (n + 127) / 128));
+    h->NS = shape_ns(n);
+    h->cap_n = n; h->cap_T = T;
     auto dalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 16)); };
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = dalloc((void**)&h->cst, sizeof(double) * c.size());
     // column parts per streaming unit: split the (long) upper part so that the first sub-blocks are ready early
-    h->nparts = (n >= 512) ? 4 : (n >= 192 ? 2 : 1);
-    if (const char* v = getenv("TAME_NPARTS")) h->nparts = std::max(1, std::min(TAME_MAX_PARTS, atoi(v)));
+    h->nparts = shape_nparts(n);
     if (e == cudaSuccess) e = dalloc((void**)&h->H, sizeof(double) * (size_t)nloc * T * 2 * cfg->r * h->nparts);
     if (e == cudaSuccess) e = dalloc((void**)&h->Craw, sizeof(double) * (size_t)nloc * T * d * d);
     if (e == cudaSuccess) e = dalloc((void**)&h->hab, sizeof(double) * (size_t)nloc * T * 2);
@@ -488,7 +515,7 @@ int tame_create(const tame_config* cfg, tame_handle** out) {
     else CK(cudaStreamSynchronize(cudaStreamLegacy));
 
     h->nb_ll = h->ops->llmse_blocks(P);
-    h->nb_cell = std::max(1, std::min(148 * 8, (int)(((long)nloc * T + 7) / 8)));
+    h->nb_cell = h->ops->cellterms_blocks(P);
     e = dalloc((void**)&h->part_ll, sizeof(double) * 2 * (size_t)h->nb_ll);
     if (e == cudaSuccess) e = dalloc((void**)&h->part_cell, sizeof(double) * 4 * (size_t)h->nb_cell);
     if (e != cudaSuccess) { tame_destroy(h); return fail(TAME_ENOMEM, "allocation failed: %s", cudaGetErrorString(e)); }
@@ -727,6 +754,10 @@ static constexpr int BATCH_FALLBACK = 1;      // internal: the device-loop path 
 static int fit_batch_device(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* Xm_dev,
                             double* const* Xc_dev, int32_t max_iter, double tolerance, double* elbo_traces, double* mse_traces,
                             int32_t* n_done, int32_t n_streams) {
+    if (n_streams <= 0) {
+        const char* v = getenv("TAME_BATCH_STREAMS");
+        n_streams = v ? atoi(v) : 16;
+    }
     const int S = std::max(1, std::min(n_streams <= 0 ? 16 : n_streams, n_fits));
     const int dev0 = cfgs[0].device;
     CK(cudaSetDevice(dev0));
@@ -747,18 +778,45 @@ static int fit_batch_device(int32_t n_fits, const tame_config* cfgs, const doubl
     if (e == cudaSuccess) e = cudaMalloc((void**)&nd_d, sizeof(int32_t) * (size_t)n_fits);
     for (int s = 0; s < S && e == cudaSuccess; ++s) e = cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking);
     if (e != cudaSuccess) { cleanup(); return fail(TAME_ENOMEM, "tame_fit_batch set-up: %s", cudaGetErrorString(e)); }
-    for (int f = 0; f < n_fits && rc == TAME_OK; ++f) {
+    // largest fits first (a fit's cost grows with n * T; the stable sort keeps equal shapes adjacent for the handle pools):
+    // the small ones fill the SMs the last large ones leave idle
+    std::vector<int> order(n_fits);
+    for (int f = 0; f < n_fits; ++f) order[f] = f;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (long)cfgs[a].n * cfgs[a].T > (long)cfgs[b].n * cfgs[b].T;
+    });
+    // one handle per (stream, r), sized for the largest n and the largest T of that r in the batch and re-pointed at each
+    // fit: creating and destroying a handle per fit costs milliseconds of host time, more than a small fit takes
+    int cap_n[TAME_MAX_R + 1] = {0}, cap_T[TAME_MAX_R + 1] = {0};
+    for (int f = 0; f < n_fits; ++f) {
+        cap_n[cfgs[f].r] = std::max(cap_n[cfgs[f].r], (int)cfgs[f].n);
+        cap_T[cfgs[f].r] = std::max(cap_T[cfgs[f].r], (int)cfgs[f].T);
+    }
+    bool shared_cap[TAME_MAX_R + 1];
+    for (int r = 1; r <= TAME_MAX_R; ++r) {
+        if (!cap_n[r]) continue;
+        // every fit needs the fused sweep (co-resident chain CTAs for all its time steps); otherwise the host loop takes over
+        if ((cap_T[r] + TAME_CHAIN_WPC - 1) / TAME_CHAIN_WPC + 1 > tame_get_ops(r)->sweep_capacity(1)) { cleanup(); return BATCH_FALLBACK; }
+        // a batch of very different shapes (large n x small T next to small n x large T) would make the common capacity
+        // much larger than any fit: keep one handle per shape then
+        const double d = 2 + 2 * r, bytes = (double)S * cap_n[r] * cap_T[r] * (3.0 * d * d + 8.0 * d) * 8.0;
+        shared_cap[r] = bytes <= 8e9;
+    }
+    for (int k = 0; k < n_fits && rc == TAME_OK; ++k) {
+        const int f = order[k];
         const tame_config& cf = cfgs[f];
-        const int s = f % S;
+        const int s = k % S;
         tame_handle* h = nullptr;
         for (tame_handle* q : pool[s])
-            if (q->cfg.n == cf.n && q->cfg.T == cf.T && q->cfg.r == cf.r) { h = q; break; }
-        if (h) rc = tame_reconfigure(h, &cf);
-        else {
-            rc = tame_create(&cf, &h);
+            if (q->cfg.r == cf.r && q->cap_n >= cf.n && q->cap_T >= cf.T) { h = q; break; }
+        if (!h) {
+            tame_config big = cf;
+            if (shared_cap[cf.r]) { big.n = cap_n[cf.r]; big.T = cap_T[cf.r]; }
+            rc = tame_create(&big, &h);
             if (rc == TAME_OK) { pool[s].push_back(h); rc = tame_set_stream(h, streams[s]); h->skip_symcheck = true; }
         }
-        if (rc == TAME_OK && f == 0 && !h->fused) { cleanup(); return BATCH_FALLBACK; }   // no fused sweep at this shape: host loop
+        if (rc == TAME_OK) rc = tame_reconfigure(h, &cf);
+        if (rc == TAME_OK && !h->fused) rc = fail(TAME_ESTATE, "tame_fit_batch: the fused sweep is unavailable for fit %d", f);
         if (rc == TAME_OK) rc = tame_bind_Y(h, Y_dev[f]);
         if (rc == TAME_OK) rc = tame_bind_state(h, Xm_dev[f], Xc_dev[f]);
         if (rc == TAME_OK) rc = tame_fit_device(h, max_iter, tolerance, el_d + (size_t)f * max_iter, ms_d + (size_t)f * max_iter, nd_d + f);

@@ -402,16 +402,15 @@ __device__ __forceinline__ double tame_gj_inverse(double (&col)[D], double* rowb
 
 // logdet of a symmetric positive-definite DxD matrix (lane c holds column c): forward elimination only -- at step k just
 // the rows below the pivot are updated (half the work of the inverse) -- and the pivots are multiplied in groups of four
-// so that 18 pivots cost 5 logarithms.  rowb: 2*(D+32) doubles.
+// so that 18 pivots cost 5 logarithms.  A GROUP of lanes owns the matrix (lane c of the group <-> column c, `act` = c < D and
+// the group has a matrix); all 32 lanes must call.  rb2: 2*D doubles of shared memory per group (double-buffered pivot row).
 template <int D>
-__device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rowb, int lane) {
-    constexpr int RB = D + 32;
-    const int slot = (lane < D) ? lane : D + (lane - D);
+__device__ __forceinline__ double tame_logdet_spd(double (&col)[D], double* rb2 /* this lane group's 2 * D doubles */, int c, bool act) {
     double logdet = 0.0, prod = 1.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        double* rb = rowb + (k & 1) * RB;
-        rb[slot] = col[k];
+        double* rb = rb2 + (k & 1) * D;
+        if (act) rb[c] = col[k];
         __syncwarp();
         const double pivv = rb[k];
         prod *= pivv;
@@ -1515,8 +1514,9 @@ __global__ void __launch_bounds__(256, 1) k_sweep(TameParams P) {
 // Same streaming tile as k_contract (TameStream).  grid (ceil(T/32), ceil(nloc/(8*RW))), block 256;
 // partial (grid.y*grid.x, 2).
 // ------------------------------------------------------------------------------------------------------
-// NW warps x RW rows = 32 rows per CTA; NW = 16, RW = 2 doubles the warps per scheduler (the kernel is issue/latency-bound,
-// ncu: long_scoreboard ~ 0, 'wait' dominant at 2 warps per scheduler) at the same ring size.
+// NW warps x RW rows = 32 rows per CTA at the same ring size.  Every warp reads each partner's record (144 B per lane at
+// r = 8) from shared memory, so the record traffic of the shared-memory pipe grows with NW: at 16 x 2 that pipe was 79 % busy
+// (ncu l1tex__data_pipe_lsu_wavefronts, short_scoreboard the top stall); 8 x 4 halves the record share (16.9 -> 14.1 ms).
 // SYM: Y was verified mirror-consistent at bind time (Y[j,i,t,:] == swap(Y[i,j,t,:]) bit for bit, which the reference's
 // generate_data guarantees, temporal_ame.py:209-216): the residuals of (j,i) are those of (i,j) swapped, so the pass only
 // streams the partners j > i and doubles the squared error.  Otherwise the full pass runs.
@@ -1866,7 +1866,7 @@ __global__ void __launch_bounds__(256, 1) k_llmse_mma(TameParams P, double* part
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_cellterms: per (i,t) block terms of the ELBO, one warp per owned cell.
+// k_cellterms: per (i,t) block terms of the ELBO, one lane group (8, 16 or 32 lanes) per owned cell.
 //   ent   = 0.5 (d (1+log 2pi) + logdet X_cov[i,t])                                    structured_mf.py:202-209
 //   t==0 : lp0 = -0.5 (logdet S0 + mu' S0inv mu + tr(S0inv X_cov) + d log 2pi)         :152-173
 //   t>0  : lpt = -0.5 (logdet Q + (mu_t - Phi mu_{t-1})' Qinv (..) + tr(Qinv X_cov) + d log 2pi)   :175-200
@@ -1876,57 +1876,72 @@ __global__ void __launch_bounds__(256, 1) k_llmse_mma(TameParams P, double* part
 template <int R>
 struct TameCellSmem {
     static constexpr int D = 2 + 2 * R;
-    double Cm[8][D * D];
-    double rowb[8][TAME_GJ_ROWB(D)];
-    double vec[8][2 * D];
+    static constexpr int DP = D <= 8 ? 8 : (D <= 16 ? 16 : 32);      // lanes per cell
+    static constexpr int G = 32 / DP;                                  // cells per warp and pass
+    double Cm[8][G * D * D];
+    double rowb[8][G * 2 * D];
+    double vec[8][G * 2 * D];
     double red[8][4];
     double cT[3][D * D];      // S0inv, Qinv, Phi transposed: cT[m][k * D + c] = M[c][k]
 };
+// A warp takes G = 32 / DP cells per pass (DP = 8, 16 or 32 lanes per cell, lane c of a group <-> column c): for the small
+// blocks of r <= 3 that is 4 cells per pass instead of 1 with 26 idle lanes.
 template <int R>
 __device__ __forceinline__ void tame_cellterms_impl(const TameParams& P, double logdetS0, double logdetQ, double* partial,
                                                     TameCellSmem<R>& sh, int bid, int nb) {
-    constexpr int D = 2 + 2 * R, NE = (D * D + 31) / 32;
+    using CS = TameCellSmem<R>;
+    constexpr int D = 2 + 2 * R, DD = D * D, DP = CS::DP, G = CS::G, NE = (G * DD + 31) / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 3 * D * D; e += blockDim.x) {
-        const int m = e / (D * D), rc = e % (D * D);
-        sh.cT[m][(rc % D) * D + rc / D] = P.cst[(m == 2 ? 5 : m) * D * D + rc];
+    const int g = lane / DP, c = lane % DP;
+    for (int e = threadIdx.x; e < 3 * DD; e += blockDim.x) {
+        const int m = e / DD, rc = e % DD;
+        sh.cT[m][(rc % D) * D + rc / D] = P.cst[(m == 2 ? 5 : m) * DD + rc];
     }
     __syncthreads();
     const double LOG2PI = 1.8378770664093454835606594728112;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const long ncell = (long)P.nloc * P.T;
-    for (long cell = (long)bid * 8 + warp; cell < ncell; cell += (long)nb * 8) {
-        const int l = (int)(cell / P.T), t = (int)(cell % P.T);
-        const int i = tame_grow(l, P.panel, P.world, P.rank);
-        const double* cp = P.Xc + ((size_t)i * P.T + t) * D * D;
+    for (long cell0 = ((long)bid * 8 + warp) * G; cell0 < ncell; cell0 += (long)nb * 8 * G) {
 #pragma unroll
         for (int m = 0; m < NE; ++m) {
-            int e = lane + 32 * m;
-            if (e < D * D) sh.Cm[warp][e] = cp[e];
+            const int e = lane + 32 * m;
+            if (e < G * DD) {
+                const long ce = cell0 + e / DD;
+                double v = 0.0;
+                if (ce < ncell) {
+                    const int le = (int)(ce / P.T), te = (int)(ce % P.T);
+                    v = P.Xc[((size_t)tame_grow(le, P.panel, P.world, P.rank) * P.T + te) * DD + e % DD];
+                }
+                sh.Cm[warp][e] = v;
+            }
         }
-        const int c = lane;
-        if (c < D) {
-            double mt = P.Xm[((size_t)i * P.T + t) * D + c];
-            sh.vec[warp][c] = mt;
-            sh.vec[warp][D + c] = (t > 0) ? P.Xm[((size_t)i * P.T + t - 1) * D + c] : 0.0;
+        const long cell = cell0 + g;
+        const bool valid = cell < ncell, act = valid && c < D;
+        const int l = valid ? (int)(cell / P.T) : 0, t = valid ? (int)(cell % P.T) : 0;
+        const int i = tame_grow(l, P.panel, P.world, P.rank);
+        double* vec = sh.vec[warp] + g * 2 * D;
+        const double* Cg = sh.Cm[warp] + g * DD;
+        if (act) {
+            vec[c] = P.Xm[((size_t)i * P.T + t) * D + c];
+            vec[D + c] = (t > 0) ? P.Xm[((size_t)i * P.T + t - 1) * D + c] : 0.0;
         }
         __syncwarp();
         const double* A = sh.cT[t == 0 ? 0 : 1];                 // S0inv or Qinv, A[k * D + c] = M[c][k]
         const double* Phi = sh.cT[2];
         double col[D];
         double tr = 0.0, trA = 0.0, resid = 0.0;
-        if (c < D) {
+        if (act) {
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                col[k] = sh.Cm[warp][k * D + c];
+                col[k] = Cg[k * D + c];
                 trA = fma(A[k * D + c], col[k], trA);       // sum_k A[c][k] * cov[k][c]
                 tr = (k == c) ? col[k] : tr;
             }
-            resid = sh.vec[warp][c];
+            resid = vec[c];
             if (t > 0) {
                 double pm = 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) pm = fma(Phi[k * D + c], sh.vec[warp][D + k], pm);
+                for (int k = 0; k < D; ++k) pm = fma(Phi[k * D + c], vec[D + k], pm);
                 resid -= pm;
             }
         } else {
@@ -1934,29 +1949,35 @@ __device__ __forceinline__ void tame_cellterms_impl(const TameParams& P, double 
             for (int k = 0; k < D; ++k) col[k] = 0.0;
         }
         __syncwarp();
-        if (c < D) sh.vec[warp][c] = resid;
+        if (act) vec[c] = resid;
         __syncwarp();
         double quad = 0.0;
-        if (c < D) {
+        if (act) {
             double a = 0.0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) a = fma(A[k * D + c], sh.vec[warp][k], a);
+            for (int k = 0; k < D; ++k) a = fma(A[k * D + c], vec[k], a);
             quad = resid * a;
         }
-        const double logdet = tame_logdet_spd<D>(col, sh.rowb[warp], lane);
+        const double logdet = tame_logdet_spd<D>(col, sh.rowb[warp] + g * 2 * D, c, act);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = DP / 2; o > 0; o >>= 1) {
             tr += __shfl_xor_sync(0xffffffffu, tr, o);
             trA += __shfl_xor_sync(0xffffffffu, trA, o);
             quad += __shfl_xor_sync(0xffffffffu, quad, o);
         }
-        if (lane == 0) {
+        if (valid && c == 0) {
             const double lp = -0.5 * ((t == 0 ? logdetS0 : logdetQ) + quad + trA + D * LOG2PI);
             if (t == 0) acc[0] += lp; else acc[1] += lp;
             acc[2] += 0.5 * (D * (1.0 + LOG2PI) + logdet);
             acc[3] += tr;
         }
         __syncwarp();
+    }
+    // the group leaders' sums -> lane 0 (the other lanes hold zeros)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o >= DP; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     }
     if (lane == 0) {
 #pragma unroll
@@ -2008,37 +2029,60 @@ __device__ __forceinline__ void tame_grid_sync(unsigned int* bar, unsigned int n
     __syncthreads();
 }
 
-// moment totals of the current means, one CTA per time step (strided), fixed summation order
+// moment totals of the current means, one CTA per time step (strided), fixed summation order: thread <-> (entry e, node
+// part p), part p sums the nodes p, p + PARTS, ... and the parts are added in order (red: PARTS * TOT doubles of smem)
 template <int R>
-__device__ __forceinline__ void tame_totals_small(const TameParams& P, int bid, int nb) {
+__device__ __forceinline__ void tame_totals_small(const TameParams& P, double* red, int bid, int nb) {
     constexpr int D = 2 + 2 * R, NV = 2 * R, TOT = TameTot<R>::TOT;
+    constexpr int PARTS = (256 / TOT) > 0 ? (256 / TOT) : 1, EPT = (TOT + 255) / 256;     // r = 2: 12 parts of 20 entries
     for (int t = bid; t < P.T; t += nb) {
-        for (int e = threadIdx.x; e < TOT; e += blockDim.x) {
-            int xa, xb = -1;
-            if (e < NV) xa = tame_zidx<R>(e);
-            else { const int f = e - NV; xa = tame_zidx<R>(f / NV); xb = tame_zidx<R>(f % NV); }
-            double acc = 0.0;
-            for (int j = 0; j < P.n; ++j) {
-                const double* m = P.Xm + ((size_t)j * P.T + t) * D;
-                const double va = __ldcg(m + xa);
-                acc += (xb < 0) ? va : va * __ldcg(m + xb);
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int slot = threadIdx.x + 256 * q, e = slot % TOT, part = slot / TOT;
+            if (part < PARTS) {
+                int xa, xb = -1;
+                if (e < NV) xa = tame_zidx<R>(e);
+                else { const int f = e - NV; xa = tame_zidx<R>(f / NV); xb = tame_zidx<R>(f % NV); }
+                double acc = 0.0;
+                for (int j = part; j < P.n; j += PARTS) {
+                    const double* m = P.Xm + ((size_t)j * P.T + t) * D;
+                    const double va = __ldcg(m + xa);
+                    acc += (xb < 0) ? va : va * __ldcg(m + xb);
+                }
+                if (PARTS == 1) P.tot[(size_t)t * TOT + e] = acc;
+                else red[part * TOT + e] = acc;
             }
-            P.tot[(size_t)t * TOT + e] = acc;
+        }
+        if (PARTS > 1) {
+            __syncthreads();
+            if (threadIdx.x < TOT) {
+                double acc = 0.0;
+#pragma unroll
+                for (int p = 0; p < PARTS; ++p) acc += red[p * TOT + threadIdx.x];
+                P.tot[(size_t)t * TOT + threadIdx.x] = acc;
+            }
+            __syncthreads();
         }
     }
 }
 
-// quadratic form of the expected log-likelihood (i<j) + squared reconstruction error (i != j): one warp per (row, 32-step
-// time slice), lane <-> t, partners in order (structured_mf.py:124-146, temporal_ame.py:255-291); per-block sums -> part[bid][0..1]
+// quadratic form of the expected log-likelihood (i<j) + squared reconstruction error (i != j): one warp per (row, W-step
+// time slice), lane <-> (t, partner subgroup): W = 8, 16 or 32 time steps per slice, whichever pads T least, and the 32 / W
+// lane groups take every (32/W)-th partner (a short T would otherwise leave most lanes idle).  Fixed summation order
+// (structured_mf.py:124-146, temporal_ame.py:255-291); per-block sums -> part[bid][0..1]
 template <int R>
 __device__ __forceinline__ void tame_llmse_small(const TameParams& P, double* part, double* red /* 16 doubles smem */, int bid, int nb) {
     constexpr int D = 2 + 2 * R;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nslices = (P.T + 31) / 32;
+    int W = 32;
+    if (((P.T + 15) / 16) * 16 < ((P.T + W - 1) / W) * W) W = 16;
+    if (((P.T + 7) / 8) * 8 < ((P.T + W - 1) / W) * W) W = 8;
+    const int G = 32 / W, tl = lane & (W - 1), js = lane / W;
+    const int nslices = (P.T + W - 1) / W;
     const long nitems = (long)P.n * nslices;
     double sq = 0.0, quad = 0.0;
     for (long item = (long)bid * 8 + warp; item < nitems; item += (long)nb * 8) {
-        const int i = (int)(item / nslices), t = (int)(item - (long)i * nslices) * 32 + lane;
+        const int i = (int)(item / nslices), t = (int)(item - (long)i * nslices) * W + tl;
         if (t < P.T) {
             const double* mi = P.Xm + ((size_t)i * P.T + t) * D;
             double ai = mi[0], bi = mi[1], Ui[R], Vi[R];
@@ -2047,12 +2091,12 @@ __device__ __forceinline__ void tame_llmse_small(const TameParams& P, double* pa
             const double* yrow = P.Y + ((size_t)i * P.n * P.T + t) * 2;
             double s = 0.0, q = 0.0;
             // partners four at a time: the loads of a group are issued before the first use (L2 latency, no ring here)
-            for (int j0 = 0; j0 < P.n; j0 += 4) {
+            for (int j0 = js; j0 < P.n; j0 += 4 * G) {
                 double2 y[4];
                 double rec[4][D];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int j = min(j0 + u, P.n - 1);
+                    const int j = min(j0 + u * G, P.n - 1);
                     y[u] = tame_ld_stream2(yrow + (size_t)j * P.T * 2);
                     const double* mj = P.Xm + ((size_t)j * P.T + t) * D;
 #pragma unroll
@@ -2060,7 +2104,7 @@ __device__ __forceinline__ void tame_llmse_small(const TameParams& P, double* pa
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + u;
+                    const int j = j0 + u * G;
                     if (j < P.n && j != i) {
                         double d0 = ai + rec[u][1], d1 = rec[u][0] + bi;
 #pragma unroll
@@ -2104,7 +2148,7 @@ __global__ void __launch_bounds__(256, 1) k_fit(TameParams P0, TameFitArgs F) {
         TameParams P = P0;
         P.epoch = P0.epoch + it + 1;                       // stamps of this sweep (hand-over tags, unit_done)
         // ---- running totals of the partner moments from the current means; reset of the sweep's counters
-        tame_totals_small<R>(P, bid, (int)nblk);
+        tame_totals_small<R>(P, reinterpret_cast<double*>(smem_raw), bid, (int)nblk);
         if (bid == 0) {
             for (int t = tid; t < P.T; t += blockDim.x) P.progress[t] = 0;
             if (tid == 0) *P.unit_counter = 0;
@@ -2174,6 +2218,7 @@ struct TameOps {
     void (*llmse)(const TameParams&, double* partial, int* nblocks, int symmetric, cudaStream_t);
     void (*cellterms)(const TameParams&, double logdetS0, double logdetQ, double* partial, int nblocks, cudaStream_t);
     int (*llmse_blocks)(const TameParams&);
+    int (*cellterms_blocks)(const TameParams&);
 };
 const TameOps* tame_get_ops(int r);
 void tame_count_launch(int n);

@@ -206,8 +206,7 @@ int chain_max_T() {
     return c;
 }
 
-constexpr int LL_RW = 2, LL_NW = 16;      // k_llmse tile: 16 warps x 2 rows
-int llmse_blocks(const TameParams& P) { return 4 * ((P.T + 31) / 32) * ((P.nloc + 15) / 16); }   // upper bound over both variants (x4: grid.z split)
+int llmse_blocks(const TameParams& P) { return 4 * ((P.T + 31) / 32) * ((P.nloc + 15) / 16); }   // upper bound over all variants (x4: grid.z split)
 
 template <int RR, bool OK = (RR % 4 == 0)>
 struct LlmseMma {
@@ -243,10 +242,14 @@ bool llmse_use_mma() {
     return R == 4;
 }
 
-void launch_llmse(const TameParams& P, double* partial, int* nblocks, int symmetric, cudaStream_t st) {
-    if (llmse_use_mma() && LlmseMma<R>::launch(P, partial, nblocks, symmetric, st)) return;
+// DFMA ring with a 32-row tile of LL_NW warps x LL_RW rows (same ring footprint for every shape).  The tile reads each
+// partner record from shared memory once per WARP, so the shared-memory pipe carries 144 B x LL_NW of records next to the
+// 512 B x 2 of Y per partner and lane: 8 warps x 4 rows halves the record share (ncu, 16 x 2: l1tex data pipe 79 % busy,
+// short_scoreboard the top stall; config 4: 16.9 -> 14.1 ms; n = 512 ... 4096, r = 2 ... 8: 0 ... -16 %).
+template <int LL_RW, int LL_NW>
+void launch_llmse_tile(const TameParams& P, double* partial, int* nblocks, int symmetric, cudaStream_t st) {
     dim3 grid((P.T + 31) / 32, (P.nloc + 31) / 32);
-    constexpr size_t smem = TameStream<R, RW>::SMEM;      // ring PD x LL_RW x 512 x 16 B == PD x RW x 256 x 16 B
+    constexpr size_t smem = TameStream<R, RW>::SMEM;      // ring PD x LL_RW x (LL_NW x 32) x 16 B == PD x RW x 256 x 16 B
     static_assert(LL_RW * LL_NW == RW * 8, "same ring footprint");
     static PerDevice configured;
     once_per_device(configured, [] {
@@ -263,6 +266,27 @@ void launch_llmse(const TameParams& P, double* partial, int* nblocks, int symmet
     tame_count_launch(1);
 }
 
+void launch_llmse(const TameParams& P, double* partial, int* nblocks, int symmetric, cudaStream_t st) {
+    if (llmse_use_mma() && LlmseMma<R>::launch(P, partial, nblocks, symmetric, st)) return;
+    launch_llmse_tile<4, 8>(P, partial, nblocks, symmetric, st);
+}
+
+// one resident wave: the kernel is latency-bound per warp (a serial elimination per cell), so a partial second wave at a
+// third of the occupancy would cost as much as the first
+int cellterms_blocks(const TameParams& P) {
+    static PerDevice cap;
+    const int dev = current_device();
+    int c = cap.v[dev].load();
+    if (c < 0) {
+        int per = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_cellterms<R>, 256, 0);
+        c = device_sms(dev) * std::max(per, 1);
+        cap.v[dev].store(c);
+    }
+    const long cells = (long)P.nloc * P.T, per_block = 8 * TameCellSmem<R>::G;
+    return (int)std::max(1L, std::min((long)c, (cells + per_block - 1) / per_block));
+}
+
 void launch_cellterms(const TameParams& P, double logdetS0, double logdetQ, double* partial, int nblocks, cudaStream_t st) {
     k_cellterms<R><<<nblocks, 256, 0, st>>>(P, logdetS0, logdetQ, partial);
     tame_count_launch(1);
@@ -273,4 +297,4 @@ void launch_cellterms(const TameParams& P, double logdetS0, double logdetQ, doub
 #define TAME_CAT(a, b) TAME_CAT2(a, b)
 extern const TameOps TAME_CAT(tame_ops_r, TAME_R) = {
     R, chain_smem_bytes(), TameTot<R>::TOT, launch_totals, launch_contract, launch_chain, launch_covblend, launch_sweep_fused, launch_fit_device, fit_grid, sweep_capacity, chain_max_T,
-    launch_llmse, launch_cellterms, llmse_blocks};
+    launch_llmse, launch_cellterms, llmse_blocks, cellterms_blocks};
