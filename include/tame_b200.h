@@ -127,8 +127,9 @@ int tame_fit_host(const tame_config* cfg, const double* Y_host, double* X_mean_h
  * doubles (row f = fit f); n_done[f] = iterations performed by fit f (early stop per fit, base.py:183-203).
  * Fits are independent Gauss-Seidel chains.  Default path (single-GPU fits with n <= 1024 on one device): every fit is ONE
  * cooperative launch of the whole-fit kernel (tame_fit_device: all iterations and the stop rule on the device), queued
- * round-robin on `n_streams` CUDA streams (0 = default 16) from the calling thread, on pooled handles; the host only waits
- * at the end.  Otherwise (or with TAME_BATCH=host): one host thread per stream runs the host-driven loop of tame_fit.
+ * largest fit first, round-robin on `n_streams` CUDA streams (0 = default 16, or TAME_BATCH_STREAMS) from the calling
+ * thread; every stream re-points ONE handle per latent dimension, sized for the largest n and T of the batch, at its fits
+ * (no allocation or device-wide synchronisation per fit); the host only waits at the end.  Otherwise (or with TAME_BATCH=host): one host thread per stream runs the host-driven loop of tame_fit.
  * The call returns when all fits are done. */
 int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const* Y_dev, double* const* X_mean_dev,
                    double* const* X_cov_dev, int32_t max_iter, double tolerance, double* elbo_traces_host,

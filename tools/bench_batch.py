@@ -6,7 +6,7 @@ n x T x ar_coefficient x rho_dyadic, r = 2, lr 0.01, max_iter 150, tolerance 1e-
 good structured mean-field.  Data come from the device generator; the timed region is the tame_fit_batch call alone
 (inputs resident, traces to the host).  Prints one JSON line; this is a side measurement, not bench.py's headline.
 
-    python tools/bench_batch.py [--streams 8] [--max-iter 150]
+    python tools/bench_batch.py [--streams 16] [--max-iter 150]
 """
 import argparse
 import ctypes as C
@@ -24,10 +24,12 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=0, help="streams of the device-loop path (0 = the library default, 16)")
     ap.add_argument("--max-iter", type=int, default=150)
     ap.add_argument("--tolerance", type=float, default=1e-4)
     args = ap.parse_args()
+    if args.streams > 0:
+        os.environ["TAME_BATCH_STREAMS"] = str(args.streams)      # read by tame_fit_batch when n_streams <= 0
     import torch
     import bench
     from tame_b200 import _lib

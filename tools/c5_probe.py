@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Probe of the whole-fit kernel: seconds per iteration of ONE small fit (no concurrency) for a few shapes, then the
-config-5 grid for a few stream counts.  python tools/c5_probe.py"""
+config-5 grid for both chain-team shapes and two stream counts (numbers: profiles/r02_summary.md).  python tools/c5_probe.py"""
 import ctypes as C, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,7 +27,9 @@ for (n, T) in [(10, 5), (10, 40), (64, 20), (256, 5), (256, 40)]:
             _lib.check(lib.tame_fit_batch(1, cfgs, Yp, Mp, Cp, it, 0.0, _lib.dptr(el), _lib.dptr(ms), nd, 0))
             torch.cuda.synchronize(dev); best = min(best, time.time() - t0)
         print(f"n={n} T={T} mode={mode}: {best*1e3:.2f} ms per fit call, {best/it*1e6:.1f} us per iteration (incl. set-up)", flush=True)
-for s in ("16", "32", "64"):
-    os.environ["TAME_BATCH_STREAMS"] = s
-    out = bench.extra_config5(lib, _lib, dev)
-    print("streams", s, round(out["seconds"], 3), out["gpu_launches"], out["early_stopped"], flush=True)
+for nh in ("2", "1"):                       # wide / narrow chain team
+    for s in ("16", "32"):
+        os.environ["TAME_NH"] = nh
+        os.environ["TAME_BATCH_STREAMS"] = s
+        out = bench.extra_config5(lib, _lib, dev)
+        print("NH", nh, "streams", s, round(out["seconds"], 3), out["gpu_launches"], out["early_stopped"], flush=True)
