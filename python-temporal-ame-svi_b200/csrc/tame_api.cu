@@ -389,6 +389,7 @@ static int tame_reconfigure(tame_handle* h, const tame_config* cfg) {
         return fail(TAME_EINVAL, "tame_reconfigure: shape (%d, %d) outside the handle's capacity (%d, %d)", cfg->n, cfg->T, h->cap_n, h->cap_T);
     if (cfg->mode < 0 || cfg->mode > 2) return fail(TAME_EINVAL, "unknown mode %d", cfg->mode);
     if (!cfg->Phi || !cfg->Qinv || !cfg->S0inv) return fail(TAME_EINVAL, "Phi/Qinv/S0inv must be given");
+    CK(cudaSetDevice(h->cfg.device));
     const std::vector<double> c = constant_block(cfg, h->d);
     if (cfg->n != h->P.n || cfg->T != h->P.T) {
         const int n = cfg->n, T = cfg->T;
@@ -906,14 +907,23 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
     std::mutex err_mu;
     std::string err_msg;
     auto worker = [&]() {
-        cudaStream_t st = nullptr;
+        std::vector<std::pair<int, cudaStream_t>> streams;     // this worker's stream on every device it has met
         int rc = TAME_OK;
-        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = fail(TAME_ECUDA, "cudaStreamCreate failed in tame_fit_batch");
         std::vector<tame_handle*> pool;           // this worker's handles, one per shape it has met
         while (rc == TAME_OK && first_rc.load() == TAME_OK) {
             const int f = next.fetch_add(1);
             if (f >= n_fits) break;
             const tame_config& cf = cfgs[f];
+            // a stream belongs to the device that was current when it was created (a new host thread starts on device 0)
+            cudaStream_t st = nullptr;
+            for (auto& ds : streams) if (ds.first == cf.device) st = ds.second;
+            if (!st) {
+                if (cudaSetDevice(cf.device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+                    rc = fail(TAME_ECUDA, "cudaStreamCreate failed in tame_fit_batch (device %d)", cf.device);
+                    break;
+                }
+                streams.emplace_back(cf.device, st);
+            }
             tame_handle* h = nullptr;
             for (tame_handle* q : pool)
                 if (q->cfg.n == cf.n && q->cfg.T == cf.T && q->cfg.r == cf.r && q->cfg.device == cf.device && cf.world == 1) { h = q; break; }
@@ -940,7 +950,7 @@ int tame_fit_batch(int32_t n_fits, const tame_config* cfgs, const double* const*
                 err_msg = g_err;
             }
         }
-        if (st) cudaStreamDestroy(st);
+        for (auto& ds : streams) { cudaSetDevice(ds.first); cudaStreamDestroy(ds.second); }
     };
     std::vector<std::thread> pool;
     for (int w = 1; w < n_streams; ++w) pool.emplace_back(worker);
