@@ -524,16 +524,31 @@ class TemporalAMEStructuredMFVI(BaseTemporalVariationalInference):
         return self.factorization
 
 
-def fit_batch(vis, max_iter: int = 100, tolerance: float = 1e-4, device=None, n_streams: int = 0):
+def fit_batch(vis, max_iter: int = 100, tolerance: float = 1e-4, device=None, n_streams: int = 0, devices=None):
     """Fit many independent VI objects in ONE call (tame_fit_batch; BASELINE config 5, the grid of
     experiments/sensitivity_analysis.py:117-183): every object gets exactly what its own `fit(max_iter, tolerance,
     verbose=False)` would give it -- history appended, state updated, per-fit early stop (base.py:183-203) -- but the
-    fits run concurrently on one GPU.  Returns the list of histories."""
+    fits run concurrently on one GPU.  `devices=[0, 1, ...]` deals the fits over several GPUs (independent fits, no
+    collective: largest first to the least loaded device), one tame_fit_batch call per device from its own host thread.
+    Returns the list of histories."""
     if not torch.cuda.is_available():
         raise RuntimeError("tame_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     vis = list(vis)
     if not vis:
         return []
+    if devices is not None and len(devices) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        from .sharding import deal_fits
+        groups = deal_fits([float(vi.n) * vi.n * vi.T for vi in vis], len(devices))
+        jobs = [(g, d) for g, d in zip(groups, devices) if g]
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:          # ctypes releases the GIL inside the C call
+            futs = [pool.submit(fit_batch, [vis[k] for k in g], max_iter, tolerance, torch.device("cuda", int(d)) if isinstance(d, int) else d, n_streams)
+                    for g, d in jobs]
+            for fu in futs:
+                fu.result()
+        return [vi.history for vi in vis]
+    if devices is not None and len(devices) == 1 and device is None:
+        device = torch.device("cuda", int(devices[0])) if isinstance(devices[0], int) else devices[0]
     lib = _lib.load()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if dev.index is None:

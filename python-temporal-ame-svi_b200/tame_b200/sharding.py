@@ -7,7 +7,7 @@ replicated.  Y is never communicated.
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Sequence, Tuple
 
 DEFAULT_PANEL = 64
 
@@ -45,3 +45,18 @@ def shard_rows(Y, panel: int, world: int, rank: int):
         return torch.cat(parts, 0)
     import numpy as np
     return np.concatenate(parts, 0)
+
+
+def deal_fits(costs: Sequence[float], n_groups: int) -> List[List[int]]:
+    """Independent fits over devices (BASELINE config 5 shards trivially): largest cost first, each to
+    the group with the smallest load so far (ties: the lowest group).  Returns the fit indices per group, each in the
+    caller's order; deterministic."""
+    if n_groups < 1:
+        raise ValueError("n_groups must be positive")
+    load = [0.0] * n_groups
+    groups: List[List[int]] = [[] for _ in range(n_groups)]
+    for f in sorted(range(len(costs)), key=lambda k: (-float(costs[k]), k)):
+        g = min(range(n_groups), key=lambda k: (load[k], k))
+        groups[g].append(f)
+        load[g] += float(costs[f])
+    return [sorted(g) for g in groups]

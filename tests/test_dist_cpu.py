@@ -14,6 +14,24 @@ from conftest import golden_constants, load_golden, rel_err
 from oracle import tame_oracle as orc
 
 
+def test_deal_fits_balances_and_is_deterministic():
+    """Independent fits over devices (BASELINE config 5): every fit exactly once, largest first to
+    the least loaded device, the caller's order inside a group."""
+    from tame_b200 import sharding as sh
+    costs = [float(n) * n * T for n in (10, 20, 32, 50, 64, 100, 160, 256) for T in (5, 10, 20, 40) for _ in range(4)]
+    for g in (1, 2, 3, 8):
+        groups = sh.deal_fits(costs, g)
+        assert len(groups) == g and sorted(k for grp in groups for k in grp) == list(range(len(costs)))
+        assert all(grp == sorted(grp) for grp in groups)
+        load = [sum(costs[k] for k in grp) for grp in groups]
+        assert max(load) - min(load) <= max(costs)              # the greedy bound
+        assert groups == sh.deal_fits(costs, g)
+    assert sh.deal_fits([], 2) == [[], []]
+    assert sh.deal_fits([3.0, 1.0, 2.0], 2) == [[0], [1, 2]]
+    with pytest.raises(ValueError):
+        sh.deal_fits([1.0], 0)
+
+
 def test_ownership_map_is_a_bijection():
     from tame_b200 import sharding as sh
     for n, panel, world in [(256, 64, 2), (200, 64, 4), (64, 64, 8), (8192, 64, 8), (130, 32, 3)]:
